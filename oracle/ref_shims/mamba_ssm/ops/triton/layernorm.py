@@ -1,0 +1,15 @@
+import torch
+
+
+class RMSNorm(torch.nn.Module):
+    def __init__(self, hidden_size, eps=1e-5, device=None, dtype=None):
+        super().__init__()
+        self.eps = eps
+        self.weight = torch.nn.Parameter(torch.ones(hidden_size, device=device, dtype=dtype))
+
+
+def layer_norm_fn(*a, **k):
+    raise NotImplementedError("generic Block wrapper is dead code in DiffMa (SURVEY 2.1 row 16)")
+
+
+rms_norm_fn = layer_norm_fn
