@@ -1,0 +1,102 @@
+"""ctypes binding of ``libdiffma_b200.so`` -- the structs and prototypes of ``include/diffma_b200.h``.
+
+This is the binding a reference-side maintainer would write (INTEGRATION.md shows it used from
+``block/mamba.py``).  No torch types cross this boundary: raw device pointers, sizes, strides and the
+stream handle.  There is NO fallback: if the library is missing and cannot be built, ``lib()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+DM_ABI_VERSION = 2
+DM_OK, DM_ERR_INVALID_ARG, DM_ERR_UNSUPPORTED, DM_ERR_CUDA = 0, -1, -2, -4
+DM_F32, DM_BF16 = 0, 1
+DM_MAX_GROUPS = 4
+DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
+
+EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba2_ssd_fwd", "dm_version", "dm_status_string", "dm_last_cuda_error",
+           "dm_build_info")
+
+
+class Mamba1Group(C.Structure):
+    _fields_ = [
+        ("xz", C.c_void_p), ("xz_batch_stride", C.c_int64), ("xz_token_stride", C.c_int64),
+        ("out", C.c_void_p), ("out_batch_stride", C.c_int64), ("out_dir_stride", C.c_int64),
+        ("out_token_stride", C.c_int64),
+        ("u", C.c_void_p), ("x_dbl", C.c_void_p),
+        ("conv_weight", C.c_void_p), ("conv_bias", C.c_void_p), ("x_proj_weight", C.c_void_p),
+        ("dt_proj_weight", C.c_void_p), ("dt_bias", C.c_void_p), ("A", C.c_void_p), ("D", C.c_void_p),
+    ]
+
+
+class Mamba1Args(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("n_dir", C.c_int32), ("seqlen", C.c_int32),
+        ("d_inner", C.c_int32), ("d_state", C.c_int32), ("dt_rank", C.c_int32), ("d_conv", C.c_int32),
+        ("act_dtype", C.c_int32), ("out_order", C.c_int32), ("n_groups", C.c_int32),
+        ("order", C.c_void_p),
+        ("group", Mamba1Group * DM_MAX_GROUPS),
+    ]
+
+
+class Mamba2Group(C.Structure):
+    _fields_ = [
+        ("zxbcdt", C.c_void_p), ("in_batch_stride", C.c_int64), ("in_token_stride", C.c_int64),
+        ("out", C.c_void_p), ("out_batch_stride", C.c_int64), ("out_dir_stride", C.c_int64),
+        ("out_token_stride", C.c_int64),
+        ("sumsq", C.c_void_p), ("sumsq_batch_stride", C.c_int64), ("sumsq_dir_stride", C.c_int64),
+        ("conv_weight", C.c_void_p), ("conv_bias", C.c_void_p), ("dt_bias", C.c_void_p), ("A", C.c_void_p),
+        ("D", C.c_void_p),
+    ]
+
+
+class Mamba2Args(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("n_dir", C.c_int32), ("seqlen", C.c_int32),
+        ("d_inner", C.c_int32), ("d_state", C.c_int32), ("nheads", C.c_int32), ("d_conv", C.c_int32),
+        ("act_dtype", C.c_int32), ("out_order", C.c_int32), ("n_groups", C.c_int32), ("gate", C.c_int32),
+        ("order", C.c_void_p),
+        ("group", Mamba2Group * DM_MAX_GROUPS),
+    ]
+
+
+_LIB = None
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdiffma_b200.so")
+
+
+def lib() -> C.CDLL:
+    """Load (building first if stale and nvcc is present) the C-ABI library.  Raises if unavailable."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    from . import build as _build
+    path = _build.ensure_built()
+    if not os.path.exists(path):
+        raise RuntimeError(f"diffma_b200: CUDA library {path} is missing and could not be built; "
+                           "there is no CPU fallback")
+    L = C.CDLL(path)
+    L.dm_version.restype = C.c_int
+    L.dm_status_string.restype = C.c_char_p
+    L.dm_status_string.argtypes = [C.c_int]
+    L.dm_last_cuda_error.restype = C.c_int
+    L.dm_build_info.restype = C.c_char_p
+    L.dm_mamba1_scan_fwd.restype = C.c_int
+    L.dm_mamba1_scan_fwd.argtypes = [C.POINTER(Mamba1Args), C.c_void_p]
+    L.dm_mamba2_ssd_fwd.restype = C.c_int
+    L.dm_mamba2_ssd_fwd.argtypes = [C.POINTER(Mamba2Args), C.c_void_p]
+    if L.dm_version() != DM_ABI_VERSION:
+        raise RuntimeError(f"diffma_b200: library ABI {L.dm_version()} != binding ABI {DM_ABI_VERSION}; rebuild")
+    _LIB = L
+    return L
+
+
+def check(status: int, what: str) -> None:
+    if status != DM_OK:
+        L = lib()
+        msg = L.dm_status_string(status).decode()
+        extra = f" (cudaError {L.dm_last_cuda_error()})" if status == DM_ERR_CUDA else ""
+        raise RuntimeError(f"{what}: {msg}{extra}")

@@ -1,0 +1,151 @@
+"""adaLN-modulated Mamba blocks with the reference's interface: ``forward(x (N,T,D), c (N,2D), w (N,T,1)) -> (N,T,D)``.
+
+Row a9 of SURVEY.md section 8 ("DiffMaBlock forward() signature").  Constructor kwargs, sub-module and parameter
+names follow reference block/mamba_block.py (Spiral :13-130, Zig :137-205, ViM :208-268, VMamba :271-340,
+EfficientVMamba :343-397, DiT :400-418) so checkpoints load.  The Spiral block hands BOTH of its mixers to
+``mixer.mix_groups`` so their three directions each run in one launch pair.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .mixer import Mamba, Mamba2, mix_groups
+
+
+def modulate(x, shift, scale):
+    return x * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+
+
+def _basic_init(module):
+    if isinstance(module, nn.Linear):
+        torch.nn.init.xavier_uniform_(module.weight)
+        if module.bias is not None:
+            nn.init.constant_(module.bias, 0)
+
+
+def _mixer(use_mamba2, D_dim, d_state, **orders):
+    cls = Mamba2 if use_mamba2 else Mamba
+    return cls(d_model=D_dim, d_state=d_state, d_conv=4, expand=2, **orders)
+
+
+class Spiral_MambaBlock(nn.Module):
+    def __init__(self, D_dim, E_dim, dt_rank, dim_inner, d_state, token_list, token_list_reversal, origina_list,
+                 origina_list_reversal, use_mamba2):
+        super().__init__()
+        self.D_dim, self.E_dim, self.dt_rank, self.dim_inner, self.d_state = D_dim, E_dim, dt_rank, dim_inner, d_state
+        orders = dict(token_list=token_list, token_list_reversal=token_list_reversal, origina_list=origina_list,
+                      origina_list_reversal=origina_list_reversal)
+        self.norm1 = nn.LayerNorm(D_dim)
+        self.mamba1 = _mixer(use_mamba2, D_dim, d_state, **orders)
+        self.mamba2 = _mixer(use_mamba2, D_dim, d_state, **orders)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(D_dim * 2, D_dim * 3, bias=True))
+        self.attention_network = nn.Sequential(nn.LayerNorm(2 * D_dim), nn.Linear(2 * D_dim, D_dim, bias=True),
+                                               nn.SiLU(), nn.Linear(D_dim, 1, bias=True), nn.Sigmoid())
+        self.sigmoid = nn.Sigmoid()
+        self.initialize_weights()
+
+    def forward(self, x, c, w):
+        shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
+        x_ssm = modulate(self.norm1(x), shift, scale)
+        w_ssm = x_ssm * w
+        a, b = mix_groups([self.mamba1, self.mamba2], [x_ssm, w_ssm], "spiral")
+        alpha = self.attention_network(torch.cat([a, b], dim=-1))
+        return x + gate.unsqueeze(1) * (alpha * a + (1 - alpha) * b)
+
+    def initialize_weights(self):
+        self.apply(_basic_init)
+        for i in (1, 3):
+            nn.init.constant_(self.attention_network[i].weight, 0)
+            nn.init.constant_(self.attention_network[i].bias, 0)
+
+
+class _SingleMixerBlock(nn.Module):
+    scan_type = ""
+
+    def __init__(self, D_dim, E_dim, dt_rank, dim_inner, d_state, use_mamba2, **orders):
+        super().__init__()
+        self.D_dim, self.E_dim, self.dt_rank, self.dim_inner, self.d_state = D_dim, E_dim, dt_rank, dim_inner, d_state
+        self.norm1 = nn.LayerNorm(D_dim)
+        self.mamba = _mixer(use_mamba2, D_dim, d_state, **orders)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(D_dim * 2, D_dim * 3, bias=True))
+        self.apply(_basic_init)
+
+    def forward(self, x, c, w):
+        shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
+        x_ssm = modulate(self.norm1(x), shift, scale)
+        return x + gate.unsqueeze(1) * self.mamba(x_ssm, self.scan_type)
+
+
+class Zig_MambaBlock(_SingleMixerBlock):
+    scan_type = "zigma"
+
+    def __init__(self, D_dim, E_dim, dt_rank, dim_inner, d_state, token_list, origina_list, use_mamba2):
+        super().__init__(D_dim, E_dim, dt_rank, dim_inner, d_state, use_mamba2, token_list=token_list,
+                         origina_list=origina_list)
+
+
+class ViM_MambaBlock(_SingleMixerBlock):
+    scan_type = "vim"
+
+    def __init__(self, D_dim, E_dim, dt_rank, dim_inner, d_state, use_mamba2):
+        super().__init__(D_dim, E_dim, dt_rank, dim_inner, d_state, use_mamba2)
+
+
+class VMamba_MambaBlock(_SingleMixerBlock):
+    scan_type = "vmamba"
+
+    def __init__(self, D_dim, E_dim, dt_rank, dim_inner, d_state, token_list, origina_list, use_mamba2):
+        super().__init__(D_dim, E_dim, dt_rank, dim_inner, d_state, use_mamba2, token_list=token_list,
+                         origina_list=origina_list)
+
+
+class EfficientVMamba_MambaBlock(_SingleMixerBlock):
+    scan_type = "eff"
+
+    def __init__(self, D_dim, E_dim, dt_rank, dim_inner, d_state, use_mamba2):
+        super().__init__(D_dim, E_dim, dt_rank, dim_inner, d_state, use_mamba2)
+
+
+class _Attention(nn.Module):
+    """timm-style multi-head self-attention (names qkv / proj as in timm.models.vision_transformer.Attention)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=True):
+        super().__init__()
+        self.num_heads = num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        q, k, v = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        return self.proj(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C))
+
+
+class _Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = nn.GELU(approximate="tanh")
+        self.fc2 = nn.Linear(hidden_features, in_features)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class DiTBlock(nn.Module):
+    """The paper's transformer baseline (reference block/mamba_block.py:400-418); not on the Mamba hot path."""
+
+    def __init__(self, hidden_size, num_heads, mlp_ratio=4.0, **block_kwargs):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.attn = _Attention(hidden_size, num_heads=num_heads, qkv_bias=True)
+        self.norm2 = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.mlp = _Mlp(hidden_size, int(hidden_size * mlp_ratio))
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size * 2, 6 * hidden_size, bias=True))
+
+    def forward(self, x, c, w):
+        s1, sc1, g1, s2, sc2, g2 = self.adaLN_modulation(c).chunk(6, dim=1)
+        x = x + g1.unsqueeze(1) * self.attn(modulate(self.norm1(x), s1, sc1))
+        return x + g2.unsqueeze(1) * self.mlp(modulate(self.norm2(x), s2, sc2))

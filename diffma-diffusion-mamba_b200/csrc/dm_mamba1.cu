@@ -1,0 +1,487 @@
+// Mamba-1 forward hot path for sm_100a (SURVEY.md section 8a rows a2 + a4, reference call sites
+// block/mamba.py:346-393 and the CrossScan/CrossMerge gathers block/mamba.py:32-82).
+//
+// Two kernels, one C-ABI call, all directions x all mixers ("groups") of a block in each launch:
+//
+//   m1_conv_xproj_kernel   one CTA per 32-token tile of one scanned sequence:
+//                          gather rows by the scan order -> causal conv1d (sliding window in registers)
+//                          -> SiLU -> u (scan order, act dtype) ; x_dbl = u . W_x^T on the legacy tensor
+//                          path (mma.sync bf16, fp32 accumulate; fp32 I/O uses the 3-term bf16 split so the
+//                          result is fp32-accurate) -> x_dbl (fp32).
+//   m1_scan_kernel         one WARP per (sequence, 32 channels), lane = channel, 16 states in registers:
+//                          per 16-token chunk: cp.async-staged x_dbl/u/z tiles (double buffered),
+//                          dt_proj on mma.sync (W_dt fragments resident in registers), then the sequential
+//                          recurrence h = exp2(dt*A*log2e) h + dt*u*B ; y = <h, C> + D u ; out = y*silu(z)
+//                          written straight to its un-permuted (token-order) row.
+//
+// Why the x_proj cut: B_t, C_t and dt_low_t are reductions over all d_inner channels of token t, so no
+// channel-sliced CTA can start scanning a token before every channel of it is convolved.  The scan is
+// MUFU-bound (16 ex2 per (b,d,l)), needs channel-sliced parallelism to fill 148 SMs, and the x_dbl
+// round trip is 256 B/token in L2 -- so the cut costs nothing measurable.
+#include "dm_common.cuh"
+
+namespace dm {
+
+namespace {
+
+constexpr int kN = 16;        // d_state
+constexpr int kW = 4;         // d_conv
+constexpr int kE = 64;        // dt_rank + 2*d_state handled by this build (R = 32)
+constexpr int kR = 32;
+constexpr int kTP = 32;       // tokens per conv/x_proj tile
+constexpr int kPThreads = 256;
+constexpr int kCH = 16;       // tokens per scan chunk
+constexpr int kSWarps = 2;    // warps per scan CTA
+
+struct M1G {
+    const void* xz;
+    int64_t xz_bs, xz_ts;
+    void* out;
+    int64_t out_bs, out_ds, out_ts;
+    void* u;
+    float* x_dbl;
+    const float* conv_w;
+    const float* conv_b;
+    const void* wx;
+    const void* wdt;
+    const float* dt_bias;
+    const float* A;
+    const float* D;
+};
+
+struct M1P {
+    int B, K, L, D;
+    int out_order, n_groups;
+    int tiles_per_seq;
+    const int32_t* order;
+    M1G g[DM_MAX_GROUPS];
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);   // .x = a (low half)
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// x ~= hi + lo with hi, lo bf16: the pair carries ~16 mantissa bits, enough for fp32-grade GEMM results
+__device__ __forceinline__ void split_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    hi = pack_bf16(__bfloat162float(ah), __bfloat162float(bh));
+    lo = pack_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+        uint2 t = *reinterpret_cast<const uint2*>(p);
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x), b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+        uint2 t;
+        t.x = pack_bf16(v[0], v[1]);
+        t.y = pack_bf16(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = t;
+    }
+};
+
+__device__ __forceinline__ const int32_t* dir_order(const M1P& p, int k) {
+    if (p.order == nullptr) return nullptr;
+    const int32_t* o = p.order + static_cast<int64_t>(k) * p.L;
+    return (__ldg(o) < 0) ? nullptr : o;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Kernel P: gather + causal conv1d + SiLU -> u ; x_dbl = u . W_x^T
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kPThreads) m1_conv_xproj_kernel(const __grid_constant__ M1P p) {
+    constexpr bool kSplit = sizeof(T) == 4;     // fp32 I/O: 3-term bf16 split on both operands
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int D = p.D;
+    const int ldu = D + 8;                       // bf16 elements per smem row; (D+8)*2 B = odd multiple of 16 B
+    __nv_bfloat16* u_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+    __nv_bfloat16* u_lo = u_hi + kTP * ldu;      // only touched when kSplit
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int seq = tile / p.tiles_per_seq, jt = tile - seq * p.tiles_per_seq;
+    const int k = seq % p.K, b = (seq / p.K) % p.B, g = seq / (p.K * p.B);
+    const M1G& G = p.g[g];
+    const int L = p.L, j0 = jt * kTP;
+    const int32_t* ord = dir_order(p, k);
+    const T* x_base = static_cast<const T*>(G.xz) + static_cast<int64_t>(b) * G.xz_bs;
+    const int64_t seq_in_group = static_cast<int64_t>(b) * p.K + k;
+    T* u_out = static_cast<T*>(G.u) + seq_in_group * L * D;
+
+    // ---- conv + SiLU: each thread owns 4 adjacent channels and slides over the tile's tokens ----
+    for (int c = tid * 4; c < D; c += kPThreads * 4) {
+        float w[4][kW], bias[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(G.conv_w + static_cast<int64_t>(c + q) * kW));
+            w[q][0] = t.x; w[q][1] = t.y; w[q][2] = t.z; w[q][3] = t.w;
+            bias[q] = G.conv_b ? __ldg(G.conv_b + c + q) : 0.f;
+        }
+        float win[3][4];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int j = j0 - 3 + t;
+            if (j >= 0) {
+                const int src = ord ? __ldg(ord + j) : j;
+                Vec4<T>::load(x_base + static_cast<int64_t>(src) * G.xz_ts + c, win[t]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) win[t][q] = 0.f;
+            }
+        }
+#pragma unroll 4
+        for (int jj = 0; jj < kTP; ++jj) {
+            const int j = j0 + jj;
+            float uv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (j < L) {
+                float xn[4];
+                const int src = ord ? __ldg(ord + j) : j;
+                Vec4<T>::load(x_base + static_cast<int64_t>(src) * G.xz_ts + c, xn);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float acc = bias[q];
+                    acc = fmaf(w[q][0], win[0][q], acc);
+                    acc = fmaf(w[q][1], win[1][q], acc);
+                    acc = fmaf(w[q][2], win[2][q], acc);
+                    acc = fmaf(w[q][3], xn[q], acc);
+                    uv[q] = silu_fast(acc);
+                    win[0][q] = win[1][q]; win[1][q] = win[2][q]; win[2][q] = xn[q];
+                }
+                Vec4<T>::store(u_out + static_cast<int64_t>(j) * D + c, uv);
+                if constexpr (!kSplit) {   // the MMA must see exactly the values the scan will read back
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) uv[q] = __bfloat162float(__float2bfloat16_rn(uv[q]));
+                }
+            }
+            uint32_t h0, h1, l0, l1;
+            split_bf16(uv[0], uv[1], h0, l0);
+            split_bf16(uv[2], uv[3], h1, l1);
+            *reinterpret_cast<uint2*>(u_hi + jj * ldu + c) = make_uint2(h0, h1);
+            if constexpr (kSplit) *reinterpret_cast<uint2*>(u_lo + jj * ldu + c) = make_uint2(l0, l1);
+        }
+    }
+    __syncthreads();
+
+    // ---- x_dbl tile (32 x 64) = u tile (32 x D) . W_x^T ; each warp takes a K-slice of D/8 channels ----
+    float acc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+
+    const int kslice = D / 8;
+    const int kbeg = warp * kslice;
+    const T* Wx = static_cast<const T*>(G.wx);
+    for (int k0 = kbeg; k0 < kbeg + kslice; k0 += 16) {
+        uint32_t a_hi[2][4], a_lo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int row = mt * 16 + (lane & 15), col = k0 + (lane >> 4) * 8;
+            ldmatrix_x4(a_hi[mt][0], a_hi[mt][1], a_hi[mt][2], a_hi[mt][3], smem_u32(u_hi + row * ldu + col));
+            if constexpr (kSplit)
+                ldmatrix_x4(a_lo[mt][0], a_lo[mt][1], a_lo[mt][2], a_lo[mt][3], smem_u32(u_lo + row * ldu + col));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const T* wp = Wx + static_cast<int64_t>(nt * 8 + (lane >> 2)) * D + k0 + 2 * (lane & 3);
+            uint32_t b_hi[2], b_lo[2];
+            if constexpr (kSplit) {
+                float2 w0 = __ldg(reinterpret_cast<const float2*>(wp));
+                float2 w1 = __ldg(reinterpret_cast<const float2*>(wp + 8));
+                split_bf16(w0.x, w0.y, b_hi[0], b_lo[0]);
+                split_bf16(w1.x, w1.y, b_hi[1], b_lo[1]);
+            } else {
+                b_hi[0] = __ldg(reinterpret_cast<const uint32_t*>(wp));
+                b_hi[1] = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma_bf16_16816(acc[mt][nt], a_hi[mt], b_hi[0], b_hi[1]);
+                if constexpr (kSplit) {
+                    mma_bf16_16816(acc[mt][nt], a_lo[mt], b_hi[0], b_hi[1]);
+                    mma_bf16_16816(acc[mt][nt], a_hi[mt], b_lo[0], b_lo[1]);
+                }
+            }
+        }
+    }
+    __syncthreads();                                   // everyone is done reading u_hi/u_lo: reuse as reduce buffer
+    float* red = reinterpret_cast<float*>(smem_raw);   // [8 warps][32][64]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int row = mt * 16 + (lane >> 2), col = nt * 8 + 2 * (lane & 3);
+            float* r = red + (warp * kTP + row) * kE + col;
+            *reinterpret_cast<float2*>(r) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+            *reinterpret_cast<float2*>(r + 8 * kE) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+        }
+    __syncthreads();
+    float* xd_out = G.x_dbl + seq_in_group * L * kE;
+    for (int o = tid * 4; o < kTP * kE; o += kPThreads * 4) {
+        const int row = o / kE;
+        if (j0 + row >= L) continue;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) {
+            float4 t = *reinterpret_cast<const float4*>(red + w8 * kTP * kE + o);
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        *reinterpret_cast<float4*>(xd_out + static_cast<int64_t>(j0) * kE + o) = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Kernel S: dt_proj + softplus + selective scan + D skip + SiLU(z) gate
+// ------------------------------------------------------------------------------------------------------
+template <typename T> struct ScanSmem {
+    float xd[2][kCH][kE];        // x_dbl chunk: [dt_low 32 | B 16 | C 16]
+    T us[2][kCH][32];
+    T zs[2][kCH][32];
+    float ds[kCH][33];           // delta_raw tile (token, channel-in-warp)
+    int rows[2][kCH];            // source / output row of each scanned token
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kSWarps * 32) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
+    constexpr bool kSplit = sizeof(T) == 4;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = blockIdx.x * kSWarps + warp;
+    if (unit >= n_units) return;
+    ScanSmem<T>& S = reinterpret_cast<ScanSmem<T>*>(smem_raw)[warp];
+
+    const int D = p.D, L = p.L;
+    const int slices = D >> 5;
+    const int cs = unit % slices, seq = unit / slices;
+    const int k = seq % p.K, b = (seq / p.K) % p.B, g = seq / (p.K * p.B);
+    const M1G& G = p.g[g];
+    const int c0 = cs * 32, c = c0 + lane;
+    const int32_t* ord = dir_order(p, k);
+    const int64_t seq_in_group = static_cast<int64_t>(b) * p.K + k;
+    const T* u_seq = static_cast<const T*>(G.u) + seq_in_group * L * D + c0;
+    const T* z_base = static_cast<const T*>(G.xz) + static_cast<int64_t>(b) * G.xz_bs + D + c0;
+    const float* xd_seq = G.x_dbl + seq_in_group * L * kE;
+    T* out_base = static_cast<T*>(G.out) + static_cast<int64_t>(b) * G.out_bs + static_cast<int64_t>(k) * G.out_ds + c;
+
+    // per-channel constants
+    float A2[kN];
+#pragma unroll
+    for (int n = 0; n < kN; n += 4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(G.A + static_cast<int64_t>(c) * kN + n));
+        A2[n] = t.x * kLog2e; A2[n + 1] = t.y * kLog2e; A2[n + 2] = t.z * kLog2e; A2[n + 3] = t.w * kLog2e;
+    }
+    const float dtb = G.dt_bias ? __ldg(G.dt_bias + c) : 0.f;
+    const float Dc = G.D ? __ldg(G.D + c) : 0.f;
+
+    // W_dt fragments (B operand, "col" layout): n = channel c0 + nt*8 + lane/4, k = ks*16 + 2*(lane%4) (+8)
+    uint32_t bw_hi[4][2][2], bw_lo[4][2][2];
+    {
+        const T* Wdt = static_cast<const T*>(G.wdt);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const T* wp = Wdt + static_cast<int64_t>(c0 + nt * 8 + (lane >> 2)) * kR + ks * 16 + 2 * (lane & 3);
+                if constexpr (kSplit) {
+                    float2 w0 = __ldg(reinterpret_cast<const float2*>(wp));
+                    float2 w1 = __ldg(reinterpret_cast<const float2*>(wp + 8));
+                    split_bf16(w0.x, w0.y, bw_hi[nt][ks][0], bw_lo[nt][ks][0]);
+                    split_bf16(w1.x, w1.y, bw_hi[nt][ks][1], bw_lo[nt][ks][1]);
+                } else {
+                    bw_hi[nt][ks][0] = __ldg(reinterpret_cast<const uint32_t*>(wp));
+                    bw_hi[nt][ks][1] = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
+                }
+            }
+    }
+
+    constexpr int kSegU = 32 * sizeof(T) / 16;       // 16-byte segments per (token, 32 channels) row
+    auto prefetch = [&](int ci) {
+        const int buf = ci & 1, j0 = ci * kCH;
+        const int nrows = min(kCH, L - j0);
+        // x_dbl rows are contiguous
+        const char* xsrc = reinterpret_cast<const char*>(xd_seq + static_cast<int64_t>(j0) * kE);
+        const uint32_t xdst = smem_u32(&S.xd[buf][0][0]);
+        for (int s = lane; s < nrows * (kE * 4 / 16); s += 32) cp_async16(xdst + s * 16, xsrc + s * 16);
+        const uint32_t udst = smem_u32(&S.us[buf][0][0]), zdst = smem_u32(&S.zs[buf][0][0]);
+        for (int s = lane; s < nrows * kSegU; s += 32) {
+            const int r = s / kSegU, part = s - r * kSegU;
+            const int j = j0 + r;
+            const int src = ord ? __ldg(ord + j) : j;
+            if (part == 0) S.rows[buf][r] = src;
+            cp_async16(udst + s * 16, reinterpret_cast<const char*>(u_seq + static_cast<int64_t>(j) * D) + part * 16);
+            cp_async16(zdst + s * 16,
+                       reinterpret_cast<const char*>(z_base + static_cast<int64_t>(src) * G.xz_ts) + part * 16);
+        }
+        cp_async_commit();
+    };
+
+    float h[kN];
+#pragma unroll
+    for (int n = 0; n < kN; ++n) h[n] = 0.f;
+
+    const int n_chunks = (L + kCH - 1) / kCH;
+    prefetch(0);
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        const int buf = ci & 1, j0 = ci * kCH;
+        if (ci + 1 < n_chunks) {
+            prefetch(ci + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+
+        // ---- delta_raw tile (16 tokens x 32 channels) = dt_low (16 x 32) . W_dt^T on mma.sync ----
+        {
+            float dacc[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dacc[nt][i] = 0.f;
+            const int r = lane >> 2, kq = 2 * (lane & 3);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const float2 v0 = *reinterpret_cast<const float2*>(&S.xd[buf][r][ks * 16 + kq]);
+                const float2 v1 = *reinterpret_cast<const float2*>(&S.xd[buf][r + 8][ks * 16 + kq]);
+                const float2 v2 = *reinterpret_cast<const float2*>(&S.xd[buf][r][ks * 16 + kq + 8]);
+                const float2 v3 = *reinterpret_cast<const float2*>(&S.xd[buf][r + 8][ks * 16 + kq + 8]);
+                uint32_t a_hi[4], a_lo[4];
+                split_bf16(v0.x, v0.y, a_hi[0], a_lo[0]);
+                split_bf16(v1.x, v1.y, a_hi[1], a_lo[1]);
+                split_bf16(v2.x, v2.y, a_hi[2], a_lo[2]);
+                split_bf16(v3.x, v3.y, a_hi[3], a_lo[3]);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    mma_bf16_16816(dacc[nt], a_hi, bw_hi[nt][ks][0], bw_hi[nt][ks][1]);
+                    // dt_low is always kept in fp32, so its low half is worth one extra MMA in both modes
+                    mma_bf16_16816(dacc[nt], a_lo, bw_hi[nt][ks][0], bw_hi[nt][ks][1]);
+                    if constexpr (kSplit) mma_bf16_16816(dacc[nt], a_hi, bw_lo[nt][ks][0], bw_lo[nt][ks][1]);
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                S.ds[r][nt * 8 + kq] = dacc[nt][0];
+                S.ds[r][nt * 8 + kq + 1] = dacc[nt][1];
+                S.ds[r + 8][nt * 8 + kq] = dacc[nt][2];
+                S.ds[r + 8][nt * 8 + kq + 1] = dacc[nt][3];
+            }
+        }
+        __syncwarp();
+
+        // ---- sequential recurrence over the chunk's tokens; lane = channel ----
+        const int nrows = min(kCH, L - j0);
+#pragma unroll 2
+        for (int jj = 0; jj < nrows; ++jj) {
+            const float dt = softplus_f(S.ds[jj][lane] + dtb);
+            const float uu = to_f32<T>(S.us[buf][jj][lane]);
+            const float zz = to_f32<T>(S.zs[buf][jj][lane]);
+            const float dtu = dt * uu;
+            const float4* bc = reinterpret_cast<const float4*>(&S.xd[buf][jj][kR]);
+            float y = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 Bq = bc[q], Cq = bc[4 + q];
+                const float Bv[4] = {Bq.x, Bq.y, Bq.z, Bq.w}, Cv[4] = {Cq.x, Cq.y, Cq.z, Cq.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int n = q * 4 + i;
+                    const float dA = ex2_approx(dt * A2[n]);
+                    h[n] = fmaf(dA, h[n], dtu * Bv[i]);
+                    y = fmaf(h[n], Cv[i], y);
+                }
+            }
+            y = fmaf(Dc, uu, y);
+            const float o = y * silu_fast(zz);
+            const int row = (p.out_order == DM_OUT_TOKEN_ORDER) ? S.rows[buf][jj] : (j0 + jj);
+            out_base[static_cast<int64_t>(row) * G.out_ts] = from_f32<T>(o);
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T>
+int launch_m1(const M1P& p, cudaStream_t stream) {
+    const int n_seq = p.n_groups * p.B * p.K;
+    const bool split = sizeof(T) == 4;
+    // kernel P
+    {
+        const size_t smem = static_cast<size_t>(kTP) * (p.D + 8) * 2 * (split ? 2 : 1);
+        const size_t red = static_cast<size_t>(8) * kTP * kE * 4;
+        const size_t bytes = smem > red ? smem : red;
+        static thread_local size_t configured = 0;
+        if (bytes > configured) {
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(bytes)));
+            configured = bytes;
+        }
+        m1_conv_xproj_kernel<T><<<n_seq * p.tiles_per_seq, kPThreads, bytes, stream>>>(p);
+        DM_CUDA_TRY(cudaGetLastError());
+    }
+    // kernel S
+    {
+        const int n_units = n_seq * (p.D / 32);
+        const size_t bytes = sizeof(ScanSmem<T>) * kSWarps;
+        static thread_local bool configured = false;
+        if (!configured) {
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(bytes)));
+            configured = true;
+        }
+        m1_scan_kernel<T><<<(n_units + kSWarps - 1) / kSWarps, kSWarps * 32, bytes, stream>>>(p, n_units);
+        DM_CUDA_TRY(cudaGetLastError());
+    }
+    return DM_OK;
+}
+
+}  // namespace
+}  // namespace dm
+
+extern "C" int dm_mamba1_scan_fwd(const dm_mamba1_args* a, void* stream) {
+    using namespace dm;
+    if (a == nullptr) return DM_ERR_INVALID_ARG;
+    if (a->batch <= 0 || a->n_dir <= 0 || a->seqlen <= 0 || a->n_groups <= 0 || a->n_groups > DM_MAX_GROUPS)
+        return DM_ERR_INVALID_ARG;
+    if (a->out_order != DM_OUT_SCAN_ORDER && a->out_order != DM_OUT_TOKEN_ORDER) return DM_ERR_INVALID_ARG;
+    if (a->act_dtype != DM_F32 && a->act_dtype != DM_BF16) return DM_ERR_UNSUPPORTED;
+    if (a->d_state != kN || a->d_conv != kW || a->dt_rank != kR) return DM_ERR_UNSUPPORTED;
+    if (a->d_inner <= 0 || a->d_inner % 128 != 0) return DM_ERR_UNSUPPORTED;
+    const size_t es = dtype_size(a->act_dtype);
+    M1P p{};
+    p.B = a->batch; p.K = a->n_dir; p.L = a->seqlen; p.D = a->d_inner;
+    p.out_order = a->out_order; p.n_groups = a->n_groups;
+    p.tiles_per_seq = (a->seqlen + kTP - 1) / kTP;
+    p.order = a->order;
+    for (int g = 0; g < a->n_groups; ++g) {
+        const dm_mamba1_group& s = a->group[g];
+        if (!s.xz || !s.out || !s.u || !s.x_dbl || !s.conv_weight || !s.x_proj_weight || !s.dt_proj_weight || !s.A)
+            return DM_ERR_INVALID_ARG;
+        if (!aligned16(s.xz) || !aligned16(s.out) || !aligned16(s.u) || !aligned16(s.x_dbl) ||
+            !aligned16(s.conv_weight) || !aligned16(s.x_proj_weight) || !aligned16(s.dt_proj_weight) || !aligned16(s.A))
+            return DM_ERR_INVALID_ARG;
+        if ((s.xz_batch_stride * es) % 16 || (s.xz_token_stride * es) % 16) return DM_ERR_INVALID_ARG;
+        if (s.xz_token_stride < 2 * a->d_inner) return DM_ERR_INVALID_ARG;
+        M1G& d = p.g[g];
+        d.xz = s.xz; d.xz_bs = s.xz_batch_stride; d.xz_ts = s.xz_token_stride;
+        d.out = s.out; d.out_bs = s.out_batch_stride; d.out_ds = s.out_dir_stride; d.out_ts = s.out_token_stride;
+        d.u = s.u; d.x_dbl = s.x_dbl;
+        d.conv_w = s.conv_weight; d.conv_b = s.conv_bias; d.wx = s.x_proj_weight; d.wdt = s.dt_proj_weight;
+        d.dt_bias = s.dt_bias; d.A = s.A; d.D = s.D;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return a->act_dtype == DM_F32 ? launch_m1<float>(p, st) : launch_m1<__nv_bfloat16>(p, st);
+}

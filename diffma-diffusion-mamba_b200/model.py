@@ -1,0 +1,211 @@
+"""``DiffMa`` and the ``DiffMa_models`` registry with the reference's interface (row a11 of SURVEY.md section 8).
+
+``DiffMa_models[name](input_size=, dt_rank=, d_state=, use_mamba2=)`` and
+``DiffMa.forward(x, t, y, y2, w)`` follow reference model.py:112-316 / :377-673 -- same constructor kwargs, same
+sub-module and parameter names (``x_embedder.proj``, ``t_embedder.mlp.{0,2}``, ``pos_embed``, ``blocks.N...``,
+``final_layer.{linear,adaLN_modulation.1}``), so a reference checkpoint's ``state_dict`` loads with
+``strict=True``.  The GPU box has no ``/root/reference``; this mirror is what bench.py and the -m gpu tests run.
+The reference's own ``model.py`` runs unchanged on top of ``shims/`` as well.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import scan_orders
+from .blocks import (DiTBlock, EfficientVMamba_MambaBlock, Spiral_MambaBlock, ViM_MambaBlock, VMamba_MambaBlock,
+                     Zig_MambaBlock, modulate)
+
+
+class PatchEmbed(nn.Module):
+    def __init__(self, img_size=28, patch_size=2, stride=2, in_chans=4, embed_dim=512, norm_layer=None, flatten=True):
+        super().__init__()
+        self.img_size = (img_size, img_size)
+        self.patch_size = (patch_size, patch_size)
+        self.grid_size = ((img_size - patch_size) // stride + 1, (img_size - patch_size) // stride + 1)
+        self.num_patches = self.grid_size[0] * self.grid_size[1]
+        self.flatten = flatten
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=self.patch_size, stride=stride)
+        self.norm = norm_layer(embed_dim) if norm_layer else nn.Identity()
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        assert H == self.img_size[0] and W == self.img_size[1], \
+            f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
+        x = self.proj(x)
+        if self.flatten:
+            x = x.flatten(2).transpose(1, 2)
+        return self.norm(x)
+
+
+class TimestepEmbed(nn.Module):
+    def __init__(self, hidden_size, frequency_embedding_size=256):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(frequency_embedding_size, hidden_size, bias=True), nn.SiLU(),
+                                 nn.Linear(hidden_size, hidden_size, bias=True))
+        self.frequency_embedding_size = frequency_embedding_size
+        self._freqs = {}
+
+    def timestep_embedding(self, t, dim, max_period=10000):
+        half = dim // 2
+        key = (str(t.device), half)
+        freqs = self._freqs.get(key)
+        if freqs is None:   # built once per device: no per-step host->device upload (reference model.py:74-76 does one)
+            freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
+            self._freqs[key] = freqs
+        args = t[:, None].float() * freqs[None]
+        emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+        if dim % 2:
+            emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+        return emb
+
+    def forward(self, t):
+        return self.mlp(self.timestep_embedding(t, self.frequency_embedding_size))
+
+
+class FinalLayer(nn.Module):
+    def __init__(self, hidden_size, patch_size, out_channels):
+        super().__init__()
+        self.norm_final = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.linear = nn.Linear(hidden_size, patch_size * patch_size * out_channels, bias=True)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size * 2, 2 * hidden_size, bias=True))
+
+    def forward(self, x, c):
+        shift, scale = self.adaLN_modulation(c).chunk(2, dim=1)
+        return self.linear(modulate(self.norm_final(x), shift, scale))
+
+
+def get_2d_sincos_pos_embed(embed_dim, grid_size):
+    """MAE sin-cos table as wired at reference model.py:325-372 (meshgrid with w first)."""
+    omega = 1.0 / 10000 ** (np.arange(embed_dim // 4, dtype=np.float64) / (embed_dim / 4.0))
+    gh, gw = np.meshgrid(np.arange(grid_size, dtype=np.float32), np.arange(grid_size, dtype=np.float32), indexing="ij")
+
+    def emb(p):
+        o = np.einsum("m,d->md", p.reshape(-1), omega)
+        return np.concatenate([np.sin(o), np.cos(o)], axis=1)
+
+    return np.concatenate([emb(gw), emb(gh)], axis=1)
+
+
+class DiffMa(nn.Module):
+    def __init__(self, input_size=28, patch_size=2, strip_size=2, in_channels=4, hidden_size=512, depth=16,
+                 learn_sigma=True, block_type="spiral", dt_rank=16, d_state=16, use_mamba2=False):
+        super().__init__()
+        self.learn_sigma, self.depth, self.in_channels = learn_sigma, depth, in_channels
+        self.out_channels = in_channels * 2 if learn_sigma else in_channels
+        self.patch_size, self.input_size, self.block_type = patch_size, input_size, block_type
+        self.x_embedder = PatchEmbed(input_size, patch_size, strip_size, in_channels, hidden_size)
+        self.t_embedder = TimestepEmbed(hidden_size)
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.x_embedder.num_patches, hidden_size), requires_grad=False)
+        n = int(input_size / patch_size)
+        common = dict(D_dim=hidden_size, E_dim=hidden_size * 2, dim_inner=hidden_size * 2, dt_rank=dt_rank,
+                      d_state=d_state, use_mamba2=use_mamba2)
+        if block_type == "spiral":
+            ml, inv = scan_orders.spiral(n)
+            self.blocks = nn.ModuleList([
+                Spiral_MambaBlock(token_list=ml[(2 * i) % len(ml)], token_list_reversal=ml[(2 * i) % len(ml) + 1],
+                                  origina_list=inv[(2 * i) % len(ml)], origina_list_reversal=inv[(2 * i) % len(ml) + 1],
+                                  **common) for i in range(depth)])
+        elif block_type == "zig":
+            self.blocks = nn.ModuleList([
+                Zig_MambaBlock(token_list=scan_orders.zig(n, i)[0], origina_list=scan_orders.zig(n, i)[1], **common)
+                for i in range(depth)])
+        elif block_type == "vim":
+            self.blocks = nn.ModuleList([ViM_MambaBlock(**common) for _ in range(depth)])
+        elif block_type == "vmamba":
+            ol, il = scan_orders.vmamba_(n)
+            self.blocks = nn.ModuleList([VMamba_MambaBlock(token_list=ol, origina_list=il, **common)
+                                         for _ in range(depth)])
+        elif block_type == "efficientVMamba":
+            self.blocks = nn.ModuleList([EfficientVMamba_MambaBlock(**common) for _ in range(depth)])
+        elif block_type == "DiT":
+            self.blocks = nn.ModuleList([DiTBlock(hidden_size=hidden_size, num_heads=8) for _ in range(depth)])
+        else:
+            raise ValueError(block_type)
+        self.final_layer = FinalLayer(hidden_size, patch_size, self.out_channels)
+        self.initialize_weights()
+
+    def initialize_weights(self):
+        def _basic_init(module):
+            if isinstance(module, nn.Linear):
+                torch.nn.init.xavier_uniform_(module.weight)
+                if module.bias is not None:
+                    nn.init.constant_(module.bias, 0)
+        self.apply(_basic_init)
+        pe = get_2d_sincos_pos_embed(self.pos_embed.shape[-1], int(self.x_embedder.num_patches ** 0.5))
+        self.pos_embed.data.copy_(torch.from_numpy(pe).float().unsqueeze(0))
+        w = self.x_embedder.proj.weight.data
+        nn.init.xavier_uniform_(w.view([w.shape[0], -1]))
+        nn.init.constant_(self.x_embedder.proj.bias, 0)
+        nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
+        nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
+        for block in self.blocks:
+            nn.init.constant_(block.adaLN_modulation[-1].weight, 0)
+            nn.init.constant_(block.adaLN_modulation[-1].bias, 0)
+        nn.init.constant_(self.final_layer.adaLN_modulation[-1].weight, 0)
+        nn.init.constant_(self.final_layer.adaLN_modulation[-1].bias, 0)
+        nn.init.constant_(self.final_layer.linear.weight, 0)
+        nn.init.constant_(self.final_layer.linear.bias, 0)
+
+    def unpatchify(self, x):
+        c, p = self.out_channels, self.x_embedder.patch_size[0]
+        h = w = int(x.shape[1] ** 0.5)
+        assert h * w == x.shape[1]
+        x = x.reshape(x.shape[0], h, w, p, p, c)
+        return torch.einsum("nhwpqc->nchpwq", x).reshape(x.shape[0], c, h * p, h * p)
+
+    def forward(self, x, t, y, y2, w):
+        """x (N,C,H,W), t (N,), y (N,D), y2 (N,T,D), w (N,T,1) -> (N, out_channels, H, W)  [model.py:264-301]"""
+        x = self.x_embedder(x) + self.pos_embed
+        t = self.t_embedder(t)
+        c = torch.cat((t + y, t + torch.mean(y2, dim=1)), dim=1)
+        outs = []
+        for i in range(self.depth):
+            if i == 0:
+                x = self.blocks[i](x, c, w)
+            elif i > self.depth / 2:
+                x = self.blocks[i](outs[-1] + outs[self.depth - i - 1], c, w)
+            else:
+                x = self.blocks[i](outs[-1], c, w)
+            outs.append(x)
+        return self.unpatchify(self.final_layer(x, c))
+
+    def forward_with_cfg(self, x, t, y, y2, w, cfg_scale):
+        half = x[: len(x) // 2]
+        combined = torch.cat([half, half], dim=0)
+        out = self.forward(combined, t, y, y2, w)
+        eps, rest = out[:, :3], out[:, 3:]
+        cond, uncond = torch.split(eps, len(eps) // 2, dim=0)
+        half_eps = uncond + cfg_scale * (cond - uncond)
+        return torch.cat([torch.cat([half_eps, half_eps], dim=0), rest], dim=1)
+
+
+_DEPTH = {"XXL": 56, "XL": 28, "L": 16, "B": 8, "S": 4, "BL": 13, "SB": 7}
+_FAMILY = {"DiffMa": "spiral", "ZigMa": "zig", "ViM": "vim", "VMamba": "vmamba", "EMamba": "efficientVMamba",
+           "DiT": "DiT"}
+
+
+def _factory(depth, patch, block_type):
+    def make(**kwargs):
+        return DiffMa(depth=depth, hidden_size=512, patch_size=patch, strip_size=patch, block_type=block_type, **kwargs)
+    return make
+
+
+def _registry():
+    reg = {}
+    sizes = {"DiffMa": ("XXL", "XL", "L", "B", "S"), "ZigMa": ("XL", "L", "B", "S"), "ViM": ("XL", "L", "B", "S"),
+             "VMamba": ("XL", "L", "B", "S"), "EMamba": ("XL", "L", "B", "S"), "DiT": ("XL", "L", "B", "S")}
+    for fam, szs in sizes.items():
+        for s in szs:
+            for p in (2, 4, 7):
+                reg[f"{fam}-{s}/{p}"] = _factory(_DEPTH[s], p, _FAMILY[fam])
+    for fam in ("ZigMa", "ViM", "VMamba", "EMamba"):
+        reg[f"{fam}-BL/2"] = _factory(_DEPTH["BL"], 2, _FAMILY[fam])
+    reg["DiT-SB/2"] = _factory(_DEPTH["SB"], 2, "DiT")
+    return reg
+
+
+DiffMa_models = _registry()

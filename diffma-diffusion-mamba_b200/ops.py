@@ -1,0 +1,397 @@
+"""Torch-facing operators over the C-ABI (``include/diffma_b200.h``) -- device memory and streams only.
+
+Two levels:
+
+* ``mamba1_scan`` / ``mamba2_ssd``: the B200-native ops.  They take tokens-major activations for one or
+  several mixers ("groups") and a ``ScanPlan`` (directions + gather table resident on the device) and run
+  ALL directions of ALL groups in one C-ABI call.  Used by ``mixer.py``.
+* ``mamba_inner_fn`` / ``mamba_split_conv1d_scan_combined`` / ``RMSNormGated`` ...: the upstream
+  ``mamba_ssm`` signatures the reference imports (block/mamba.py:11, block/mamba2.py:17-21), implemented on
+  top of the ops above.  ``shims/`` re-exports them under the upstream module paths.
+
+There is no CPU path: every op raises on non-CUDA tensors (the oracle lives in ``oracle/`` and is test-only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import _cabi
+
+__all__ = ["ScanPlan", "mamba1_scan", "mamba2_ssd", "mamba_inner_fn", "selective_scan_fn", "causal_conv1d_fn",
+           "mamba_split_conv1d_scan_combined", "mamba_chunk_scan_combined", "RMSNormGated"]
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _cabi.DM_F32
+    if t.dtype == torch.bfloat16:
+        return _cabi.DM_BF16
+    raise TypeError(f"diffma_b200 kernels take fp32 or bf16 activations, got {t.dtype} "
+                    "(the reference's fp16 autocast maps to bf16 here, see DESIGN.md)")
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: diffma_b200 has no CPU path (tensor on {t.device}); "
+                           "use oracle/ for CPU reference values in tests")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream_handle(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+# --------------------------------------------------------------------------------------------------
+# direction plans
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class ScanPlan:
+    """How one mixer call scans its tokens (reference semantics: SURVEY.md App. A.4).
+
+    ``table``  int32 device tensor (n_dir, seqlen): scanned token j of direction k is source token
+               ``table[k, j]``; a row starting with -1 is the identity; ``None`` = all identity.
+    ``layout`` where the per-direction outputs go:
+               "concat"   token-order rows, directions side by side: (B, L_src, n_dir, D) -> the merge of
+                          CrossMerge (block/mamba.py:60-82) becomes a sum over the direction axis, which the
+                          out-projection absorbs;
+               "disjoint" token-order rows, directions cover disjoint token sets (EfficientVMamba): (B, L_src, D);
+               "stacked"  scan-order rows per direction: (B, n_dir, seqlen, D) (what mamba_inner_fn returns).
+    """
+    n_dir: int
+    seqlen: int
+    src_len: int
+    table: Optional[torch.Tensor]
+    layout: str
+
+    @property
+    def out_order(self) -> int:
+        return _cabi.DM_OUT_SCAN_ORDER if self.layout == "stacked" else _cabi.DM_OUT_TOKEN_ORDER
+
+    def out_shape(self, batch: int, d: int):
+        if self.layout == "concat":
+            return (batch, self.src_len, self.n_dir, d)
+        if self.layout == "disjoint":
+            return (batch, self.src_len, d)
+        return (batch, self.n_dir, self.seqlen, d)
+
+    def out_strides(self, d: int):
+        """(batch, dir, token) strides in elements."""
+        if self.layout == "concat":
+            return (self.src_len * self.n_dir * d, d, self.n_dir * d)
+        if self.layout == "disjoint":
+            return (self.src_len * d, 0, d)
+        return (self.n_dir * self.seqlen * d, self.seqlen * d, d)
+
+    @staticmethod
+    def build(orders: Sequence[Optional[Sequence[int]]], src_len: int, layout: str, device) -> "ScanPlan":
+        """``orders``: one gather list per direction (``None`` = identity)."""
+        n_dir = len(orders)
+        lens = {len(o) for o in orders if o is not None}
+        assert len(lens) <= 1, "all directions of a call must have the same length"
+        seqlen = lens.pop() if lens else src_len
+        if all(o is None for o in orders):
+            table = None
+        else:
+            rows = []
+            for o in orders:
+                if o is None:
+                    assert seqlen == src_len
+                    rows.append(torch.full((seqlen,), -1, dtype=torch.int32))
+                else:
+                    r = torch.as_tensor(list(o), dtype=torch.int64)
+                    assert r.numel() == seqlen and int(r.min()) >= 0 and int(r.max()) < src_len
+                    rows.append(r.to(torch.int32))
+            table = torch.stack(rows).contiguous().to(device)
+        return ScanPlan(n_dir, seqlen, src_len, table, layout)
+
+
+# --------------------------------------------------------------------------------------------------
+# Mamba-1
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class Mamba1Weights:
+    conv_weight: torch.Tensor       # (D, W) fp32
+    conv_bias: Optional[torch.Tensor]
+    x_proj_weight: torch.Tensor     # (R+2N, D) act dtype
+    dt_proj_weight: torch.Tensor    # (D, R) act dtype
+    dt_bias: Optional[torch.Tensor]  # (D) fp32
+    A: torch.Tensor                 # (D, N) fp32 = -exp(A_log)
+    D: Optional[torch.Tensor]       # (D) fp32
+
+
+def _chk(t: Optional[torch.Tensor], dtype, shape, name):
+    if t is None:
+        return None
+    if t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous() or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected contiguous CUDA {dtype} {tuple(shape)}, got {t.dtype} "
+                           f"{tuple(t.shape)} contiguous={t.is_contiguous()} on {t.device}")
+    return t
+
+
+def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan,
+                    keep_intermediates: bool = False):
+    """One C-ABI call: conv1d+SiLU -> x_proj -> dt_proj -> softplus -> scan -> D skip -> SiLU(z) gate.
+
+    xz[g]: (B, L_src, 2D) tokens-major (last-dim stride 1).  Returns (out, u, x_dbl) lists; ``out[g]`` has
+    ``plan.out_shape``; u/x_dbl are the saved intermediates (scratch unless ``keep_intermediates``).
+    """
+    G = len(xz)
+    assert 1 <= G <= _cabi.DM_MAX_GROUPS and len(weights) == G
+    x0 = xz[0]
+    _require_cuda(x0, "mamba1_scan")
+    B, Lsrc, D2 = x0.shape
+    D = D2 // 2
+    assert Lsrc == plan.src_len, f"plan built for {plan.src_len} source tokens, got {Lsrc}"
+    N = weights[0].A.shape[1]
+    E = weights[0].x_proj_weight.shape[0]
+    R = E - 2 * N
+    a = _cabi.Mamba1Args()
+    a.batch, a.n_dir, a.seqlen = B, plan.n_dir, plan.seqlen
+    a.d_inner, a.d_state, a.dt_rank, a.d_conv = D, N, R, weights[0].conv_weight.shape[1]
+    a.act_dtype, a.out_order, a.n_groups = _dtype_code(x0), plan.out_order, G
+    a.order = _ptr(plan.table)
+    obs, ods, ots = plan.out_strides(D)
+    outs, us, xds = [], [], []
+    # one allocation per kind so groups are adjacent (lets callers view them as a batch)
+    out_all = torch.empty((G,) + plan.out_shape(B, D), dtype=x0.dtype, device=x0.device)
+    u_all = torch.empty((G, B, plan.n_dir, plan.seqlen, D), dtype=x0.dtype, device=x0.device)
+    xd_all = torch.empty((G, B, plan.n_dir, plan.seqlen, E), dtype=torch.float32, device=x0.device)
+    for g in range(G):
+        x, w = xz[g], weights[g]
+        if x.shape != x0.shape or x.dtype != x0.dtype or x.stride(2) != 1:
+            raise RuntimeError("mamba1_scan: every group needs the same (B, L, 2D) shape/dtype, channel stride 1")
+        gs = a.group[g]
+        gs.xz, gs.xz_batch_stride, gs.xz_token_stride = x.data_ptr(), x.stride(0), x.stride(1)
+        gs.out, gs.out_batch_stride, gs.out_dir_stride, gs.out_token_stride = out_all[g].data_ptr(), obs, ods, ots
+        gs.u, gs.x_dbl = u_all[g].data_ptr(), xd_all[g].data_ptr()
+        gs.conv_weight = _chk(w.conv_weight, torch.float32, (D, a.d_conv), "conv_weight").data_ptr()
+        gs.conv_bias = _ptr(_chk(w.conv_bias, torch.float32, (D,), "conv_bias"))
+        gs.x_proj_weight = _chk(w.x_proj_weight, x0.dtype, (E, D), "x_proj_weight").data_ptr()
+        gs.dt_proj_weight = _chk(w.dt_proj_weight, x0.dtype, (D, R), "dt_proj_weight").data_ptr()
+        gs.dt_bias = _ptr(_chk(w.dt_bias, torch.float32, (D,), "dt_bias"))
+        gs.A = _chk(w.A, torch.float32, (D, N), "A").data_ptr()
+        gs.D = _ptr(_chk(w.D, torch.float32, (D,), "D"))
+        outs.append(out_all[g]); us.append(u_all[g]); xds.append(xd_all[g])
+    st = _cabi.lib().dm_mamba1_scan_fwd(C.byref(a), C.c_void_p(_stream_handle(x0.device)))
+    _cabi.check(st, "dm_mamba1_scan_fwd")
+    return out_all, u_all, xd_all
+
+
+def mamba1_scan(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan) -> torch.Tensor:
+    """-> (G,) + plan.out_shape.  Forward only for now (inference / sampling); the backward op hooks in here."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in xz):
+        from . import autograd_ops
+        return autograd_ops.Mamba1ScanFn.apply(plan, len(xz), *xz, *autograd_ops.flatten_weights(weights))
+    return mamba1_scan_raw(xz, weights, plan)[0]
+
+
+# --------------------------------------------------------------------------------------------------
+# Mamba-2
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class Mamba2Weights:
+    conv_weight: torch.Tensor       # (D + 2N, W) fp32
+    conv_bias: Optional[torch.Tensor]
+    dt_bias: Optional[torch.Tensor]  # (H) fp32
+    A: torch.Tensor                 # (H) fp32 = -exp(A_log)
+    D: Optional[torch.Tensor]       # (H) fp32
+
+
+def mamba2_ssd_raw(zxbcdt: List[torch.Tensor], weights: List[Mamba2Weights], plan: ScanPlan, d_inner: int,
+                   d_state: int, nheads: int, gate: bool = True, want_sumsq: bool = True):
+    """One C-ABI call: conv1d+SiLU over x|B|C -> softplus(dt) -> SSD recurrence -> D skip -> SiLU(z) gate.
+
+    Returns (v, sumsq): v (G,)+plan.out_shape ; sumsq (G, B, n_dir, rows) fp32 = sum_c v^2 addressed like v's
+    rows (rows = L_src for token-order layouts, seqlen for "stacked"), or None.
+    """
+    G = len(zxbcdt)
+    assert 1 <= G <= _cabi.DM_MAX_GROUPS and len(weights) == G
+    x0 = zxbcdt[0]
+    _require_cuda(x0, "mamba2_ssd")
+    B, Lsrc, Cin = x0.shape
+    assert Lsrc == plan.src_len and Cin == 2 * d_inner + 2 * d_state + nheads
+    a = _cabi.Mamba2Args()
+    a.batch, a.n_dir, a.seqlen = B, plan.n_dir, plan.seqlen
+    a.d_inner, a.d_state, a.nheads, a.d_conv = d_inner, d_state, nheads, weights[0].conv_weight.shape[1]
+    a.act_dtype, a.out_order, a.n_groups, a.gate = _dtype_code(x0), plan.out_order, G, int(gate)
+    a.order = _ptr(plan.table)
+    obs, ods, ots = plan.out_strides(d_inner)
+    v_all = torch.empty((G,) + plan.out_shape(B, d_inner), dtype=x0.dtype, device=x0.device)
+    rows = plan.seqlen if plan.layout == "stacked" else plan.src_len
+    ss_all = torch.zeros((G, B, plan.n_dir, rows), dtype=torch.float32, device=x0.device) if want_sumsq else None
+    Cc = d_inner + 2 * d_state
+    for g in range(G):
+        x, w = zxbcdt[g], weights[g]
+        if x.shape != x0.shape or x.dtype != x0.dtype or x.stride(2) != 1:
+            raise RuntimeError("mamba2_ssd: every group needs the same (B, L, C) shape/dtype, channel stride 1")
+        gs = a.group[g]
+        gs.zxbcdt, gs.in_batch_stride, gs.in_token_stride = x.data_ptr(), x.stride(0), x.stride(1)
+        gs.out, gs.out_batch_stride, gs.out_dir_stride, gs.out_token_stride = v_all[g].data_ptr(), obs, ods, ots
+        if want_sumsq:
+            gs.sumsq, gs.sumsq_batch_stride, gs.sumsq_dir_stride = ss_all[g].data_ptr(), plan.n_dir * rows, rows
+        gs.conv_weight = _chk(w.conv_weight, torch.float32, (Cc, a.d_conv), "conv_weight").data_ptr()
+        gs.conv_bias = _ptr(_chk(w.conv_bias, torch.float32, (Cc,), "conv_bias"))
+        gs.dt_bias = _ptr(_chk(w.dt_bias, torch.float32, (nheads,), "dt_bias"))
+        gs.A = _chk(w.A, torch.float32, (nheads,), "A").data_ptr()
+        gs.D = _ptr(_chk(w.D, torch.float32, (nheads,), "D"))
+    st = _cabi.lib().dm_mamba2_ssd_fwd(C.byref(a), C.c_void_p(_stream_handle(x0.device)))
+    _cabi.check(st, "dm_mamba2_ssd_fwd")
+    return v_all, ss_all
+
+
+def mamba2_ssd(zxbcdt, weights, plan, d_inner, d_state, nheads, gate=True, want_sumsq=True):
+    if torch.is_grad_enabled() and any(t.requires_grad for t in zxbcdt):
+        raise NotImplementedError("diffma_b200: the Mamba-2 backward kernel is not built yet (forward/sampling only)")
+    return mamba2_ssd_raw(zxbcdt, weights, plan, d_inner, d_state, nheads, gate, want_sumsq)
+
+
+# --------------------------------------------------------------------------------------------------
+# upstream-signature operators (what block/mamba.py and block/mamba2.py import)
+# --------------------------------------------------------------------------------------------------
+def _autocast_dtype(x: torch.Tensor):
+    if torch.is_autocast_enabled():
+        dt = torch.get_autocast_dtype("cuda")
+        if dt == torch.float16:
+            raise TypeError("diffma_b200: fp16 autocast is not supported, use torch.autocast('cuda', torch.bfloat16)")
+        return dt
+    return x.dtype
+
+
+def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
+                   out_proj_bias, A, B=None, C=None, D=None, delta_bias=None, B_proj_bias=None,
+                   C_proj_bias=None, delta_softplus=True):
+    """[upstream mamba_ssm.ops.selective_scan_interface.mamba_inner_fn]; call sites block/mamba.py:346-393.
+
+    xz (B, 2D, L) in the reference's channel-major layout -> (B, L, d_model).  Same mixed-precision
+    rule as upstream's ``custom_fwd``: under autocast the projection weights and activations run in the
+    autocast dtype; conv weights, A, D, delta_bias stay fp32.
+    """
+    if B is not None or C is not None or B_proj_bias is not None or C_proj_bias is not None:
+        raise NotImplementedError("diffma_b200.mamba_inner_fn: only input-dependent B and C without projection "
+                                  "biases are supported (all DiffMa uses)")
+    if not delta_softplus:
+        raise NotImplementedError("diffma_b200.mamba_inner_fn: delta_softplus=False is never used by DiffMa")
+    _require_cuda(xz, "mamba_inner_fn")
+    if xz.stride(-1) != 1 and xz.stride(1) != 1:
+        raise RuntimeError("mamba_inner_fn: xz must have unit stride along L or along channels")
+    act = _autocast_dtype(xz)
+    Bsz, D2, L = xz.shape
+    xz_t = xz.to(act).transpose(1, 2)
+    if xz_t.stride(2) != 1:
+        xz_t = xz_t.contiguous()                       # channel-major -> tokens-major (one copy)
+    w = Mamba1Weights(
+        conv_weight=conv1d_weight.reshape(conv1d_weight.shape[0], -1).float().contiguous(),
+        conv_bias=None if conv1d_bias is None else conv1d_bias.float().contiguous(),
+        x_proj_weight=x_proj_weight.to(act).contiguous(), dt_proj_weight=delta_proj_weight.to(act).contiguous(),
+        dt_bias=None if delta_bias is None else delta_bias.float().contiguous(),
+        A=A.float().contiguous(), D=None if D is None else D.float().contiguous())
+    plan = ScanPlan(1, L, L, None, "stacked")
+    with torch.autocast("cuda", enabled=False):
+        y = mamba1_scan([xz_t], [w], plan)[0][:, 0]     # (B, L, D)
+        return F.linear(y, out_proj_weight.to(act), None if out_proj_bias is None else out_proj_bias.to(act))
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      return_last_state=False):
+    """[upstream selective_scan_fn] -- imported at block/mamba.py:11 but only reached with
+    ``use_fast_path=False``, which no DiffMa block ever sets."""
+    raise NotImplementedError("diffma_b200: selective_scan_fn with a precomputed delta is a dead path in DiffMa "
+                              "(use_fast_path is always True); use mamba_inner_fn")
+
+
+def causal_conv1d_fn(x, weight, bias=None, seq_idx=None, initial_states=None, return_final_states=False,
+                     final_states_out=None, activation=None):
+    """[upstream causal_conv1d.causal_conv1d_fn] -- reached only on the non-fused paths DiffMa never takes."""
+    raise NotImplementedError("diffma_b200: standalone causal_conv1d_fn is a dead path in DiffMa; the conv is "
+                              "fused into mamba_inner_fn / mamba_split_conv1d_scan_combined")
+
+
+def causal_conv1d_update(*args, **kwargs):
+    raise NotImplementedError("diffma_b200: single-token decode (step()) is never used by a diffusion model")
+
+
+def mamba_split_conv1d_scan_combined(zxbcdt, conv1d_weight, conv1d_bias, dt_bias, A, D, chunk_size,
+                                     initial_states=None, seq_idx=None, dt_limit=(0.0, float("inf")),
+                                     return_final_states=False, activation="silu", rmsnorm_weight=None,
+                                     rmsnorm_eps=1e-6, outproj_weight=None, outproj_bias=None, headdim=None,
+                                     ngroups=1, norm_before_gate=True):
+    """[upstream ssd_combined.mamba_split_conv1d_scan_combined]; call sites block/mamba2.py:392-696.
+
+    zxbcdt (B, L, 2*d_in + 2*N + H) -> (B, L, d_model).  ``chunk_size`` only tiles the upstream kernels; any
+    chunking yields the same recurrence, so it is accepted and ignored.
+    """
+    if initial_states is not None or seq_idx is not None or return_final_states:
+        raise NotImplementedError("diffma_b200: initial_states / seq_idx / final states are never used by DiffMa")
+    if tuple(dt_limit) != (0.0, float("inf")):
+        raise NotImplementedError("diffma_b200: dt_limit clamping is never used by DiffMa")
+    if activation not in ("silu", "swish") or ngroups != 1:
+        raise NotImplementedError("diffma_b200: only activation=silu, ngroups=1")
+    if rmsnorm_weight is not None and norm_before_gate:
+        raise NotImplementedError("diffma_b200: norm_before_gate=True is never used by DiffMa")
+    if D.dim() != 1:
+        raise NotImplementedError("diffma_b200: D must be per-head (H,)")
+    _require_cuda(zxbcdt, "mamba_split_conv1d_scan_combined")
+    act = _autocast_dtype(zxbcdt)
+    H = D.shape[0]
+    assert headdim is not None
+    d_in = H * headdim
+    Bsz, L, Cin = zxbcdt.shape
+    N = (Cin - 2 * d_in - H) // 2
+    z_in = zxbcdt.to(act)
+    if z_in.stride(2) != 1:
+        z_in = z_in.contiguous()
+    w = Mamba2Weights(conv_weight=conv1d_weight.reshape(conv1d_weight.shape[0], -1).float().contiguous(),
+                      conv_bias=None if conv1d_bias is None else conv1d_bias.float().contiguous(),
+                      dt_bias=None if dt_bias is None else dt_bias.float().contiguous(),
+                      A=A.float().contiguous(), D=D.float().contiguous())
+    plan = ScanPlan(1, L, L, None, "stacked")
+    with torch.autocast("cuda", enabled=False):
+        v, ss = mamba2_ssd([z_in], [w], plan, d_in, N, H, gate=True, want_sumsq=rmsnorm_weight is not None)
+        v = v[0][:, 0]                                                     # (B, L, d_in)
+        if rmsnorm_weight is not None:
+            rstd = torch.rsqrt(ss[0][:, 0] / d_in + rmsnorm_eps)           # (B, L)
+            v = (v.float() * rstd.unsqueeze(-1) * rmsnorm_weight.float()).to(act)
+        if outproj_weight is not None:
+            v = F.linear(v, outproj_weight.to(act), None if outproj_bias is None else outproj_bias.to(act))
+        return v
+
+
+def mamba_chunk_scan_combined(*args, **kwargs):
+    """[upstream mamba_chunk_scan_combined] -- imported at block/mamba2.py:20, reached only with
+    ``use_mem_eff_path=False``, which DiffMa never sets."""
+    raise NotImplementedError("diffma_b200: mamba_chunk_scan_combined is a dead path in DiffMa "
+                              "(use_mem_eff_path is always True)")
+
+
+class RMSNormGated(torch.nn.Module):
+    """[upstream layernorm_gated.RMSNorm] parameter holder used at block/mamba2.py:347-350; its weight and
+    eps are handed to ``mamba_split_conv1d_scan_combined``.  ``forward`` (never called on DiffMa's fused
+    path) computes rmsnorm(x * silu(z)) * weight with torch ops on the device."""
+
+    def __init__(self, hidden_size, eps=1e-5, norm_before_gate=True, group_size=None, device=None, dtype=None):
+        super().__init__()
+        self.eps = eps
+        self.weight = torch.nn.Parameter(torch.ones(hidden_size, device=device, dtype=dtype))
+        self.register_parameter("bias", None)
+        self.group_size = group_size
+        self.norm_before_gate = norm_before_gate
+
+    def forward(self, x, z=None):
+        _require_cuda(x, "RMSNormGated")
+        xf = x.float()
+        if z is not None and not self.norm_before_gate:
+            xf = xf * F.silu(z.float())
+        gs = self.group_size or xf.shape[-1]
+        g = xf.reshape(*xf.shape[:-1], -1, gs)
+        out = (g * torch.rsqrt(g.square().mean(-1, keepdim=True) + self.eps)).reshape(xf.shape) * self.weight.float()
+        if z is not None and self.norm_before_gate:
+            out = out * F.silu(z.float())
+        return out.to(x.dtype)

@@ -1,0 +1,147 @@
+/*
+ * diffma_b200 C-ABI -- the drop-in boundary of the B200-native DiffMa hot path.
+ *
+ * What it replaces.  The reference (wongzbb/DiffMa-Diffusion-Mamba) reaches its native code through
+ * the Python import surface of two third-party wheels:
+ *
+ *   block/mamba.py:11     from mamba_ssm.ops.selective_scan_interface import selective_scan_fn, mamba_inner_fn
+ *   block/mamba.py:13     from causal_conv1d import causal_conv1d_fn, causal_conv1d_update
+ *   block/mamba2.py:17    from mamba_ssm.ops.triton.layernorm_gated import RMSNorm as RMSNormGated
+ *   block/mamba2.py:20-21 from mamba_ssm.ops.triton.ssd_combined import mamba_chunk_scan_combined,
+ *                                                                        mamba_split_conv1d_scan_combined
+ *
+ * Beneath those wrappers upstream binds two pybind11 modules, `selective_scan_cuda.{fwd,bwd}` and
+ * `causal_conv1d_cuda.{causal_conv1d_fwd,causal_conv1d_bwd}`, plus Triton kernels for Mamba-2.  The
+ * entry points below are what a binding for this path uses instead: plain pointers and sizes, no torch
+ * types, no exceptions.  INTEGRATION.md shows the ctypes stub on the reference side.
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, a negative dm_status otherwise; never throw, never exit;
+ *   - never allocate, never synchronise, never copy host<->device: the caller owns every buffer
+ *     (scratch included, passed as named fields) and the work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), so every call is CUDA-graph capturable;
+ *   - re-entrant; the only global state is one-time cudaFuncSetAttribute per kernel;
+ *   - activations are "tokens-major": element (b, token, channel) of a tensor lives at
+ *     base + b*batch_stride + token*token_stride + channel  (strides in ELEMENTS, channel stride 1).
+ *     Callers holding the reference's (B, C, L) layout transpose first (the Python shim does);
+ *   - activation pointers must be 16-byte aligned and their strides multiples of 16 bytes.
+ */
+#ifndef DIFFMA_B200_H
+#define DIFFMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_ABI_VERSION 2
+
+typedef enum {
+    DM_OK = 0,
+    DM_ERR_INVALID_ARG = -1,   /* null pointer, bad size, misaligned pointer/stride                      */
+    DM_ERR_UNSUPPORTED = -2,   /* shape/dtype combination this build has no kernel for                   */
+    DM_ERR_CUDA = -4           /* a CUDA runtime call failed; see dm_last_cuda_error()                   */
+} dm_status;
+
+typedef enum { DM_F32 = 0, DM_BF16 = 1 } dm_dtype;
+
+#define DM_MAX_GROUPS 4
+
+/* Row placement of per-direction outputs. */
+#define DM_OUT_SCAN_ORDER 0    /* row j of direction k  = j-th scanned token  (what mamba_inner_fn returns) */
+#define DM_OUT_TOKEN_ORDER 1   /* row order[k][j]: already un-permuted, so merging directions is a plain sum */
+
+/* ------------------------------------------------------------------------------------------------------
+ * Mamba-1 forward: causal conv1d + SiLU -> x_proj -> dt_proj -> softplus -> selective scan -> D skip ->
+ * SiLU(z) gate.  Replaces, for one or several directions in one call, the part of upstream
+ * `MambaInnerFn.forward` between the in-projection and the out-projection (reference call sites
+ * block/mamba.py:346-393): causal_conv1d_cuda.causal_conv1d_fwd + two cuBLAS GEMMs +
+ * selective_scan_cuda.fwd, and the CrossScan / CrossMerge gathers around them (block/mamba.py:32-82).
+ *
+ * One "group" = one mixer (its own weights and activations).  A Spiral block has two mixers on two
+ * inputs (block/mamba_block.py:107-108); passing both as groups runs them in one launch.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    /* activations in */
+    const void* xz;            /* (B, L_src, 2*d_inner) act dtype: x = channels [0,d_inner), z = [d_inner,2*d_inner) */
+    int64_t xz_batch_stride, xz_token_stride;
+    /* activations out */
+    void* out;                 /* y * silu(z), act dtype; element (b,k,row,c) at
+                                  b*out_batch_stride + k*out_dir_stride + row*out_token_stride + c        */
+    int64_t out_batch_stride, out_dir_stride, out_token_stride;
+    /* intermediates, written by the forward, kept by the caller for the backward (or reused as scratch) */
+    void* u;                   /* (B, n_dir, seqlen, d_inner) act dtype, contiguous: silu(conv1d(x)) in scan order */
+    float* x_dbl;              /* (B, n_dir, seqlen, dt_rank + 2*d_state) fp32, contiguous: [dt_low | B | C]        */
+    /* weights */
+    const float* conv_weight;  /* (d_inner, d_conv) fp32   -- conv1d.weight viewed (d, w)                 */
+    const float* conv_bias;    /* (d_inner) fp32 or NULL                                                  */
+    const void* x_proj_weight; /* (dt_rank + 2*d_state, d_inner) act dtype, row-major                     */
+    const void* dt_proj_weight;/* (d_inner, dt_rank) act dtype, row-major                                 */
+    const float* dt_bias;      /* (d_inner) fp32 or NULL  -- `delta_bias`                                 */
+    const float* A;            /* (d_inner, d_state) fp32 -- already -exp(A_log)                          */
+    const float* D;            /* (d_inner) fp32 or NULL                                                  */
+} dm_mamba1_group;
+
+typedef struct {
+    int32_t batch;             /* B                                                                       */
+    int32_t n_dir;             /* scanned sequences per batch element (spiral 3, zig 1, vim 2, vmamba/eff 4) */
+    int32_t seqlen;            /* tokens per scanned sequence (L, or L/4 for the EfficientVMamba split)    */
+    int32_t d_inner, d_state, dt_rank, d_conv;
+    int32_t act_dtype;         /* dm_dtype of xz / out / u / x_proj / dt_proj                             */
+    int32_t out_order;         /* DM_OUT_SCAN_ORDER or DM_OUT_TOKEN_ORDER                                 */
+    int32_t n_groups;          /* 1..DM_MAX_GROUPS                                                        */
+    const int32_t* order;      /* device (n_dir, seqlen) gather table: scanned token j of direction k is
+                                  source token order[k*seqlen+j]; NULL = every direction is the identity.
+                                  A first entry order[k*seqlen] == -1 marks direction k as the identity.   */
+    dm_mamba1_group group[DM_MAX_GROUPS];
+} dm_mamba1_args;
+
+int dm_mamba1_scan_fwd(const dm_mamba1_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Mamba-2 forward: split [z | x | B | C | dt] -> causal conv1d + SiLU over [x|B|C] -> softplus(dt + bias)
+ * -> SSD state recurrence S_t = exp(dt A_h) S_{t-1} + dt x_t (x) B_t,  y_t = S_t C_t + D_h x_t
+ * -> gate v = y * silu(z), and the per-token sum of squares of v that the gated RMSNorm needs.
+ * Replaces the part of upstream `mamba_split_conv1d_scan_combined` before the RMSNorm scale and the
+ * out-projection (reference call sites block/mamba2.py:392-696): causal_conv1d_fwd + the five Triton SSD
+ * kernels + the first pass of `_layer_norm_fwd_1pass_kernel`.  ngroups = 1, norm_before_gate = False.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* zxbcdt;        /* (B, L_src, 2*d_inner + 2*d_state + nheads) act dtype                    */
+    int64_t in_batch_stride, in_token_stride;
+    void* out;                 /* v = y * silu(z), act dtype, addressed like dm_mamba1_group.out           */
+    int64_t out_batch_stride, out_dir_stride, out_token_stride;
+    float* sumsq;              /* fp32, ZEROED BY THE CALLER, or NULL to skip: sum_c v[b,k,row,c]^2 (fp32 v, before
+                                  rounding), one value per OUTPUT row, at b*sumsq_batch_stride +
+                                  k*sumsq_dir_stride + row (row as in `out`: scanned index or source token) */
+    int64_t sumsq_batch_stride, sumsq_dir_stride;
+    const float* conv_weight;  /* (d_inner + 2*d_state, d_conv) fp32                                      */
+    const float* conv_bias;    /* (d_inner + 2*d_state) fp32 or NULL                                      */
+    const float* dt_bias;      /* (nheads) fp32 or NULL                                                   */
+    const float* A;            /* (nheads) fp32 -- already -exp(A_log)                                    */
+    const float* D;            /* (nheads) fp32 or NULL                                                   */
+} dm_mamba2_group;
+
+typedef struct {
+    int32_t batch, n_dir, seqlen;
+    int32_t d_inner, d_state, nheads, d_conv;     /* headdim = d_inner / nheads                           */
+    int32_t act_dtype, out_order, n_groups;
+    int32_t gate;              /* 1: out = y * silu(z); 0: out = y (caller gates)                          */
+    const int32_t* order;      /* as in dm_mamba1_args                                                    */
+    dm_mamba2_group group[DM_MAX_GROUPS];
+} dm_mamba2_args;
+
+int dm_mamba2_ssd_fwd(const dm_mamba2_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------ */
+int dm_version(void);                     /* DM_ABI_VERSION of the loaded library                        */
+const char* dm_status_string(int status);
+int dm_last_cuda_error(void);             /* cudaError_t of the last DM_ERR_CUDA on this thread           */
+const char* dm_build_info(void);          /* "sm_100a nvcc 12.9 ..."                                      */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFMA_B200_H */
