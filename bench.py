@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Headline benchmark: diffusion-step images/s of DiffMa on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model DiffMa-B/2]
+                    [--batch 16] [--input-size 28] [--mamba2]
+
+A "step" is one denoising step (``p_sample``: the whole DiffMa forward + posterior update) over one batch of
+synthetic latents, bf16 autocast, captured as a CUDA graph.  N>1 (torchrun): every rank runs the same per-GPU
+batch on its own latents (weak scaling, no data-path collective -- sampling shards by batch).
+
+``value``       device-resident images/s over all ranks (CUDA events, barrier + synchronize both sides, max over ranks)
+``e2e``         same step through the public API with HOST (pinned) inputs: H2D of x/t/y/y2/w, step, D2H of the sample
+``roofline``    the dominant kernel (m1_scan_kernel / m2_ssd_kernel) timed alone at the workload's shape with L2 flushes
+``cpu_baseline`` the oracle (restatement of the reference's CPU selective_scan_ref path) on the host cores, N=1 only
+``--impl reference``  times that CPU path with all host threads on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "diffusion_step_images_per_s"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="DiffMa-B/2")
+    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch")
+    ap.add_argument("--input-size", type=int, default=28, help="latent side; 28 = 224x224 images (L=196), 56 -> L=784")
+    ap.add_argument("--mamba2", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from diffma_b200.model import _DEPTH
+    fam, rest = args.model.split("-")
+    size, patch = rest.split("/")
+    L = (args.input_size // int(patch)) ** 2
+    return {"workload": f"{args.model} {'mamba2' if args.mamba2 else 'mamba1'} 1 denoise step (p_sample), "
+                        f"{args.input_size}x{args.input_size}x4 latents (224x224 images at 28), L={L} tokens, "
+                        f"per-GPU batch {args.batch}, bf16 autocast",
+            "model": args.model, "depth": _DEPTH[size], "tokens": L, "per_gpu_batch": args.batch,
+            "mixer": "mamba2" if args.mamba2 else "mamba1", "respacing": "250",
+            "l2_policy": "working set per step (bf16 weights + activations) exceeds the 126 MB L2; "
+                         "kernel microbench flushes L2 explicitly between iterations"}
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl" if args.impl == "ours" else "gloo", rank=rank, world_size=world)
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+
+
+def max_over_ranks(x, world, device):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ----------------------------------------------------------------------------------------------------
+def build_model(args, device):
+    from diffma_b200 import create_model_and_diffusion, synth
+    torch.manual_seed(0)
+    net, diffusion = create_model_and_diffusion(args.model, input_size=args.input_size, use_mamba2=args.mamba2,
+                                                respacing="250")
+    synth.fill_trained_like_(net, seed=11)
+    return net.to(device).eval(), diffusion
+
+
+def kernel_roofline(args, device, peaks):
+    """Time the dominant kernel alone at the workload's per-block shape (2 mixers x 3 directions x batch)."""
+    from diffma_b200 import _cabi, ops, scan_orders
+    import ctypes as C
+    patch = int(args.model.split("/")[1])
+    n = args.input_size // patch
+    L, B, D = n * n, args.batch, 1024
+    ml, _ = scan_orders.spiral(n)
+    plan = ops.ScanPlan.build([None, ml[0], ml[1]], L, "concat", device)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    iters = 20
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    res = {}
+    if not args.mamba2:
+        xz = [torch.randn(B, L, 2 * D, generator=g).to(device, torch.bfloat16) for _ in range(2)]
+        w = [ops.Mamba1Weights((torch.randn(D, 4, generator=g) * 0.4).to(device), torch.zeros(D, device=device),
+                               (torch.randn(64, D, generator=g) / 32).to(device, torch.bfloat16),
+                               (torch.randn(D, 32, generator=g) / 5.6).to(device, torch.bfloat16),
+                               (torch.randn(D, generator=g) - 3).to(device),
+                               -torch.exp(torch.log(torch.arange(1, 17).float()).expand(D, 16)
+                                          + 0.3 * torch.randn(D, 16, generator=g)).contiguous().to(device),
+                               torch.ones(D, device=device)) for _ in range(2)]
+        a, keep = ops.mamba1_args(xz, w, plan)
+        lib, st = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        for phase, name in ((1, "m1_conv_xproj_kernel"), (2, "m1_scan_kernel")):
+            for _ in range(3):
+                _cabi.check(lib.dm_mamba1_scan_phase(C.byref(a), phase, st), "phase")
+            for i in range(iters):
+                flush.zero_()
+                ev[i][0].record()
+                lib.dm_mamba1_scan_phase(C.byref(a), phase, st)
+                ev[i][1].record()
+            torch.cuda.synchronize(device)
+            res[name] = sorted(e0.elapsed_time(e1) for e0, e1 in ev)[iters // 2] * 1e-3
+        token_scans = 2 * B * 3 * L
+        # algorithmic bytes of the scan kernel per token-scan: read u, z (2*D*2 B) + x_dbl (64*4 B),
+        # write y*silu(z) (D*2 B)
+        bytes_per = 3 * D * 2 + 256
+        dom, t = "m1_scan_kernel", res["m1_scan_kernel"]
+        exps = token_scans * D * 20           # 16 decays + softplus (2) + silu(z) (2) MUFU ops per (token, channel)
+    else:
+        Cin = 2 * D + 32 + 16
+        zx = [torch.randn(B, L, Cin, generator=g).to(device, torch.bfloat16) for _ in range(2)]
+        w = [ops.Mamba2Weights((torch.randn(D + 32, 4, generator=g) * 0.4).to(device), torch.zeros(D + 32, device=device),
+                               (torch.randn(16, generator=g) - 3).to(device),
+                               -(1 + 15 * torch.rand(16, generator=g)).to(device), torch.ones(16, device=device))
+             for _ in range(2)]
+        for _ in range(3):
+            ops.mamba2_ssd_raw(zx, w, plan, D, 16, 16)
+        for i in range(iters):
+            flush.zero_()
+            ev[i][0].record()
+            ops.mamba2_ssd_raw(zx, w, plan, D, 16, 16)       # includes the sumsq memset (tiny)
+            ev[i][1].record()
+        torch.cuda.synchronize(device)
+        res["m2_ssd_kernel"] = sorted(e0.elapsed_time(e1) for e0, e1 in ev)[iters // 2] * 1e-3
+        token_scans = 2 * B * 3 * L
+        bytes_per = (2 * D + 32 + 16) * 2 + D * 2     # read z, x, B, C, dt ; write v
+        dom, t = "m2_ssd_kernel", res["m2_ssd_kernel"]
+        exps = token_scans * D * 6
+    achieved = token_scans * bytes_per / t / 1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    sm_mhz = peaks.get("sm_max_mhz", 1965.0)
+    mufu_peak = 148 * 16 * sm_mhz * 1e6
+    return {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback B200_PROFILING.md",
+            "launch_us": {k: round(v * 1e6, 2) for k, v in res.items()},
+            "token_scans_per_launch": token_scans, "algorithmic_bytes_per_token_scan": bytes_per,
+            "binding_pipe": "mufu" if not args.mamba2 else "fp32",
+            "mufu": {"achieved_gexp_s": round(exps / t / 1e9, 1), "peak_gexp_s": round(mufu_peak / 1e9, 1),
+                     "frac": round(exps / t / mufu_peak, 4),
+                     "note": "148 SM x 16 MUFU/clk x sm_max_mhz; the scan is instruction-bound on this pipe (DESIGN.md)"}}
+
+
+def cpu_oracle_rate(args, budget_s, threads=None):
+    """images/s of the oracle (CPU restatement of the reference path, fp32, sequential scan) on a bounded sample."""
+    from diffma_b200 import synth
+    from oracle import ref_model
+    from diffma_b200.model import DiffMa_models, _DEPTH
+    if threads:
+        torch.set_num_threads(threads)
+    size, patch = args.model.split("-")[1].split("/")
+    depth, patch = _DEPTH[size], int(patch)
+    torch.manual_seed(0)
+    net = DiffMa_models[args.model](input_size=args.input_size, dt_rank=16, d_state=16, use_mamba2=args.mamba2)
+    synth.fill_trained_like_(net, seed=11)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    L = (args.input_size // patch) ** 2
+    bs = 1
+    b = synth.synthetic_batch(bs, input_size=args.input_size, tokens=L, seed=3)
+    grid = args.input_size // patch
+    x = torch.randn(bs, L, 512)
+    c = torch.randn(bs, 1024)
+    orders = ref_model.block_orders("spiral", grid, 0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        ref_model.block_ref(sd, "blocks.0.", "spiral", x, c, b["w"], orders, args.mamba2)
+        t_block = time.perf_counter() - t0
+    # how many blocks of the model fit the budget; the rest is extrapolated linearly (blocks are identical in cost)
+    nb = max(1, min(depth, int(budget_s / max(t_block, 1e-3))))
+
+    def step():
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            if nb == depth:
+                ref_model.diffma_forward_ref(sd, dict(depth=depth, patch_size=patch, block_type="spiral",
+                                                      use_mamba2=args.mamba2), b["x"], b["t"], b["y"], b["y2"], b["w"])
+                return time.perf_counter() - t0
+            h = x
+            for i in range(nb):
+                h = ref_model.block_ref(sd, f"blocks.{i}.", "spiral", h, c, b["w"],
+                                        ref_model.block_orders("spiral", grid, i), args.mamba2)
+            return (time.perf_counter() - t0) * depth / nb
+    sample = (f"oracle (torch CPU fp32, sequential selective_scan_ref) on batch {bs}: "
+              f"{nb} of {depth} blocks per step" + ("" if nb == depth else f", time scaled x{depth}/{nb}")
+              + ("" if nb < depth else " + embed/final layers"))
+    return step, bs, sample, torch.get_num_threads()
+
+
+def run_reference(args, world, rank):
+    if rank != 0:
+        return
+    total_budget = 150.0
+    per_step = total_budget / max(1, args.steps + args.warmup)
+    step, bs, sample, threads = cpu_oracle_rate(args, per_step)
+    for _ in range(args.warmup):
+        step()
+    ts = [step() for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    v = bs / t
+    cfg = workload(args)
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference = the repo's CPU oracle port of the reference's selective_scan_ref/mamba_inner_ref path "
+                    "(the reference's own CUDA wheels mamba_ssm 2.0.4 / causal_conv1d 1.2.2 are not installable offline "
+                    "and ship no sm_100 code; see DESIGN.md)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    world, rank, local = dist_setup(args)
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    from diffma_b200 import _cabi, ops
+    from diffma_b200.diffusion import GraphedSampler
+    _cabi.lib()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+
+    net, diffusion = build_model(args, device)
+    from diffma_b200 import synth
+    patch = int(args.model.split("/")[1])
+    L = (args.input_size // patch) ** 2
+    host = synth.synthetic_batch(args.batch, input_size=args.input_size, tokens=L, seed=100 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    dev_in = {k: v.to(device) for k, v in host.items()}
+    kw = dict(y=dev_in["y"], y2=dev_in["y2"], w=dev_in["w"])
+
+    def model_fn(x, t, **kwargs):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return net(x, t, **kwargs).float()
+
+    shape = tuple(dev_in["x"].shape)
+    ops.LAUNCH_COUNTER["kernels"] = 0
+    sampler = GraphedSampler(diffusion, model_fn, shape, kw, device, clip_denoised=False, warmup=2,
+                             use_graph=not args.no_graph)
+    launches_per_step = sampler.kernels_per_step
+
+    # ---- device-resident timing --------------------------------------------------------------------
+    sampler.reset(dev_in["x"])
+    for _ in range(max(3, args.warmup)):
+        sampler.step()
+    torch.cuda.synchronize(device)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        torch.cuda.synchronize(device)
+        e0.record()
+        for _ in range(args.steps):
+            sampler.step()
+        e1.record()
+        torch.cuda.synchronize(device)
+    barrier(world)
+    t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3, world, device)
+    value = world * args.batch * args.steps / t_dev
+
+    # ---- end to end through the public API with host buffers ------------------------------------
+    out_host = torch.empty(shape, dtype=torch.float32).pin_memory()
+    t_host = torch.full((args.batch,), diffusion.num_timesteps - 1, dtype=torch.long).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if v is not host["t"]) + t_host.numel() * 8
+    d2h = out_host.numel() * 4
+
+    def e2e_step():
+        sampler.load(host["x"], t_host, {"y": host["y"], "y2": host["y2"], "w": host["w"]})   # pinned H2D, async
+        sampler.step()
+        out_host.copy_(sampler.x, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier(world)
+    torch.cuda.synchronize(device)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize(device)
+    barrier(world)
+    t_e2e = max_over_ranks(e0.elapsed_time(e1) * 1e-3, world, device)
+    e2e_value = world * args.batch * args.steps / t_e2e
+
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(t_dev / args.steps * 1e3, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload(args),
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(t_e2e / args.steps * 1e3, 4)},
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "cuda_graph": not args.no_graph, "clocks": clocks.summary()}
+    if rank == 0:
+        line["roofline"] = kernel_roofline(args, device, peaks)
+        if world == 1 and not args.no_cpu_baseline:
+            step, bs, sample, threads = cpu_oracle_rate(args, 12.0)
+            step()
+            t = min(step(), step())
+            line["cpu_baseline"] = {"value": round(bs / t, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": sample + "; best of 2 after 1 warm-up", "host_cpus": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,7 @@ DM_F32, DM_BF16 = 0, 1
 DM_MAX_GROUPS = 4
 DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
-EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba2_ssd_fwd", "dm_version", "dm_status_string", "dm_last_cuda_error",
+EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba2_ssd_fwd", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
 
@@ -86,6 +86,8 @@ def lib() -> C.CDLL:
     L.dm_build_info.restype = C.c_char_p
     L.dm_mamba1_scan_fwd.restype = C.c_int
     L.dm_mamba1_scan_fwd.argtypes = [C.POINTER(Mamba1Args), C.c_void_p]
+    L.dm_mamba1_scan_phase.restype = C.c_int
+    L.dm_mamba1_scan_phase.argtypes = [C.POINTER(Mamba1Args), C.c_int, C.c_void_p]
     L.dm_mamba2_ssd_fwd.restype = C.c_int
     L.dm_mamba2_ssd_fwd.argtypes = [C.POINTER(Mamba2Args), C.c_void_p]
     if L.dm_version() != DM_ABI_VERSION:

@@ -415,11 +415,11 @@ __global__ void __launch_bounds__(kSWarps * 32) m1_scan_kernel(const __grid_cons
 }
 
 template <typename T>
-int launch_m1(const M1P& p, cudaStream_t stream) {
+int launch_m1(const M1P& p, int phases, cudaStream_t stream) {
     const int n_seq = p.n_groups * p.B * p.K;
     const bool split = sizeof(T) == 4;
     // kernel P
-    {
+    if (phases & 1) {
         const size_t smem = static_cast<size_t>(kTP) * (p.D + 8) * 2 * (split ? 2 : 1);
         const size_t red = static_cast<size_t>(8) * kTP * kE * 4;
         const size_t bytes = smem > red ? smem : red;
@@ -433,7 +433,7 @@ int launch_m1(const M1P& p, cudaStream_t stream) {
         DM_CUDA_TRY(cudaGetLastError());
     }
     // kernel S
-    {
+    if (phases & 2) {
         const int n_units = n_seq * (p.D / 32);
         const size_t bytes = sizeof(ScanSmem<T>) * kSWarps;
         static thread_local bool configured = false;
@@ -451,7 +451,7 @@ int launch_m1(const M1P& p, cudaStream_t stream) {
 }  // namespace
 }  // namespace dm
 
-extern "C" int dm_mamba1_scan_fwd(const dm_mamba1_args* a, void* stream) {
+static int m1_dispatch(const dm_mamba1_args* a, int phases, void* stream) {
     using namespace dm;
     if (a == nullptr) return DM_ERR_INVALID_ARG;
     if (a->batch <= 0 || a->n_dir <= 0 || a->seqlen <= 0 || a->n_groups <= 0 || a->n_groups > DM_MAX_GROUPS)
@@ -483,5 +483,12 @@ extern "C" int dm_mamba1_scan_fwd(const dm_mamba1_args* a, void* stream) {
         d.dt_bias = s.dt_bias; d.A = s.A; d.D = s.D;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return a->act_dtype == DM_F32 ? launch_m1<float>(p, st) : launch_m1<__nv_bfloat16>(p, st);
+    return a->act_dtype == DM_F32 ? launch_m1<float>(p, phases, st) : launch_m1<__nv_bfloat16>(p, phases, st);
+}
+
+extern "C" int dm_mamba1_scan_fwd(const dm_mamba1_args* a, void* stream) { return m1_dispatch(a, 3, stream); }
+
+extern "C" int dm_mamba1_scan_phase(const dm_mamba1_args* a, int phase, void* stream) {
+    if (phase != 1 && phase != 2) return DM_ERR_INVALID_ARG;
+    return m1_dispatch(a, phase, stream);
 }

@@ -266,44 +266,66 @@ class GraphedSampler:
     Static buffers: ``x`` (latents, updated in place by the graph), ``t`` (step index, decremented
     inside the graph) and the conditioning tensors.  ``run(noise)`` replays the graph
     ``num_timesteps`` times: no host->device copy and no Python-side kernel launch per step.
+    ``load(...)`` copies host (pinned) inputs into the static buffers for callers that stream batches in.
     """
 
     def __init__(self, diffusion: SpacedDiffusion, model: Callable, shape, model_kwargs: dict, device,
-                 clip_denoised: bool = False, warmup: int = 2):
+                 clip_denoised: bool = False, warmup: int = 2, use_graph: bool = True):
+        from . import ops
         self.diffusion, self.model = diffusion, model
         self.x = torch.zeros(*shape, device=device)
         self.t = torch.zeros(shape[0], dtype=torch.long, device=device)
         self.kw = {k: v.clone() for k, v in model_kwargs.items()}
         self.clip = clip_denoised
+        self.noise = torch.zeros(*shape, device=device)
         diffusion._tables(device)
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(warmup):
+            for _ in range(max(1, warmup)):
                 self.t.fill_(diffusion.num_timesteps - 1)
+                n0 = ops.LAUNCH_COUNTER["kernels"]
                 self._step()
+                self.kernels_per_step = ops.LAUNCH_COUNTER["kernels"] - n0
         torch.cuda.current_stream(device).wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph), torch.no_grad():
-            self._step()
+        torch.cuda.synchronize(device)
+        self.graph = None
+        if use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self._step()
 
     def _step(self):
         out = self.diffusion.p_sample(self.model, self.x, self.t, clip_denoised=self.clip, model_kwargs=self.kw)
         self.x.copy_(out["sample"])
-        self.t.sub_(1)
+        self.t.sub_(1).clamp_(min=0)
 
     def step(self):
-        self.graph.replay()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            with torch.no_grad():
+                self._step()
 
-    @torch.no_grad()
-    def run(self, noise: torch.Tensor, model_kwargs: Optional[dict] = None) -> torch.Tensor:
+    def reset(self, noise: torch.Tensor, model_kwargs: Optional[dict] = None):
         self.x.copy_(noise)
         if model_kwargs is not None:
             for k, v in model_kwargs.items():
                 self.kw[k].copy_(v)
         self.t.fill_(self.diffusion.num_timesteps - 1)
+
+    def load(self, x_host: torch.Tensor, t_host: torch.Tensor, kw_host: dict):
+        """Asynchronous H2D of one step's inputs (pinned host tensors) into the static buffers."""
+        self.x.copy_(x_host, non_blocking=True)
+        self.t.copy_(t_host, non_blocking=True)
+        for k, v in kw_host.items():
+            self.kw[k].copy_(v, non_blocking=True)
+
+    @torch.no_grad()
+    def run(self, noise: torch.Tensor, model_kwargs: Optional[dict] = None) -> torch.Tensor:
+        self.reset(noise, model_kwargs)
         for _ in range(self.diffusion.num_timesteps):
-            self.graph.replay()
+            self.step()
         return self.x.clone()
 
 

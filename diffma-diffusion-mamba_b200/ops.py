@@ -136,13 +136,21 @@ def _chk(t: Optional[torch.Tensor], dtype, shape, name):
     return t
 
 
-def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan,
-                    keep_intermediates: bool = False):
-    """One C-ABI call: conv1d+SiLU -> x_proj -> dt_proj -> softplus -> scan -> D skip -> SiLU(z) gate.
+# kernels of OURS launched so far (bench.py reports it as gpu_launches; CUDA-graph replays are counted by the
+# sampler as captured launches x replays)
+LAUNCH_COUNTER = {"kernels": 0}
 
-    xz[g]: (B, L_src, 2D) tokens-major (last-dim stride 1).  Returns (out, u, x_dbl) lists; ``out[g]`` has
-    ``plan.out_shape``; u/x_dbl are the saved intermediates (scratch unless ``keep_intermediates``).
-    """
+
+def _strides(x: torch.Tensor):
+    """(batch, token) strides in elements, normalised for size-1 dimensions (whose torch strides are arbitrary)."""
+    ts = x.stride(1) if x.shape[1] > 1 else x.shape[2]
+    bs = x.stride(0) if x.shape[0] > 1 else x.shape[1] * ts
+    return bs, ts
+
+
+def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan):
+    """Fill a ``dm_mamba1_args`` for the given groups.  Returns (args, (out, u, x_dbl)); the tensors own the memory
+    the struct points at and must outlive the launch."""
     G = len(xz)
     assert 1 <= G <= _cabi.DM_MAX_GROUPS and len(weights) == G
     x0 = xz[0]
@@ -159,7 +167,6 @@ def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: 
     a.act_dtype, a.out_order, a.n_groups = _dtype_code(x0), plan.out_order, G
     a.order = _ptr(plan.table)
     obs, ods, ots = plan.out_strides(D)
-    outs, us, xds = [], [], []
     # one allocation per kind so groups are adjacent (lets callers view them as a batch)
     out_all = torch.empty((G,) + plan.out_shape(B, D), dtype=x0.dtype, device=x0.device)
     u_all = torch.empty((G, B, plan.n_dir, plan.seqlen, D), dtype=x0.dtype, device=x0.device)
@@ -169,7 +176,8 @@ def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: 
         if x.shape != x0.shape or x.dtype != x0.dtype or x.stride(2) != 1:
             raise RuntimeError("mamba1_scan: every group needs the same (B, L, 2D) shape/dtype, channel stride 1")
         gs = a.group[g]
-        gs.xz, gs.xz_batch_stride, gs.xz_token_stride = x.data_ptr(), x.stride(0), x.stride(1)
+        gs.xz = x.data_ptr()
+        gs.xz_batch_stride, gs.xz_token_stride = _strides(x)
         gs.out, gs.out_batch_stride, gs.out_dir_stride, gs.out_token_stride = out_all[g].data_ptr(), obs, ods, ots
         gs.u, gs.x_dbl = u_all[g].data_ptr(), xd_all[g].data_ptr()
         gs.conv_weight = _chk(w.conv_weight, torch.float32, (D, a.d_conv), "conv_weight").data_ptr()
@@ -179,10 +187,20 @@ def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: 
         gs.dt_bias = _ptr(_chk(w.dt_bias, torch.float32, (D,), "dt_bias"))
         gs.A = _chk(w.A, torch.float32, (D, N), "A").data_ptr()
         gs.D = _ptr(_chk(w.D, torch.float32, (D,), "D"))
-        outs.append(out_all[g]); us.append(u_all[g]); xds.append(xd_all[g])
-    st = _cabi.lib().dm_mamba1_scan_fwd(C.byref(a), C.c_void_p(_stream_handle(x0.device)))
+    return a, (out_all, u_all, xd_all)
+
+
+def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan):
+    """One C-ABI call: conv1d+SiLU -> x_proj -> dt_proj -> softplus -> scan -> D skip -> SiLU(z) gate.
+
+    xz[g]: (B, L_src, 2D) tokens-major (last-dim stride 1).  Returns (out, u, x_dbl), each with a leading group
+    axis: ``out[g]`` has ``plan.out_shape``; u (scan order) and x_dbl are the intermediates the backward reads.
+    """
+    a, bufs = mamba1_args(xz, weights, plan)
+    st = _cabi.lib().dm_mamba1_scan_fwd(C.byref(a), C.c_void_p(_stream_handle(xz[0].device)))
     _cabi.check(st, "dm_mamba1_scan_fwd")
-    return out_all, u_all, xd_all
+    LAUNCH_COUNTER["kernels"] += 2
+    return bufs
 
 
 def mamba1_scan(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan) -> torch.Tensor:
@@ -233,7 +251,8 @@ def mamba2_ssd_raw(zxbcdt: List[torch.Tensor], weights: List[Mamba2Weights], pla
         if x.shape != x0.shape or x.dtype != x0.dtype or x.stride(2) != 1:
             raise RuntimeError("mamba2_ssd: every group needs the same (B, L, C) shape/dtype, channel stride 1")
         gs = a.group[g]
-        gs.zxbcdt, gs.in_batch_stride, gs.in_token_stride = x.data_ptr(), x.stride(0), x.stride(1)
+        gs.zxbcdt = x.data_ptr()
+        gs.in_batch_stride, gs.in_token_stride = _strides(x)
         gs.out, gs.out_batch_stride, gs.out_dir_stride, gs.out_token_stride = v_all[g].data_ptr(), obs, ods, ots
         if want_sumsq:
             gs.sumsq, gs.sumsq_batch_stride, gs.sumsq_dir_stride = ss_all[g].data_ptr(), plan.n_dir * rows, rows
@@ -244,6 +263,7 @@ def mamba2_ssd_raw(zxbcdt: List[torch.Tensor], weights: List[Mamba2Weights], pla
         gs.D = _ptr(_chk(w.D, torch.float32, (nheads,), "D"))
     st = _cabi.lib().dm_mamba2_ssd_fwd(C.byref(a), C.c_void_p(_stream_handle(x0.device)))
     _cabi.check(st, "dm_mamba2_ssd_fwd")
+    LAUNCH_COUNTER["kernels"] += 1
     return v_all, ss_all
 
 

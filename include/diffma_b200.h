@@ -100,6 +100,10 @@ typedef struct {
 
 int dm_mamba1_scan_fwd(const dm_mamba1_args* args, void* stream);
 
+/* The two kernels of dm_mamba1_scan_fwd separately, for profiling and the backward's recomputation:
+ * phase 1 = gather + conv1d + SiLU + x_proj (writes u, x_dbl); phase 2 = dt_proj + scan + gate (reads them). */
+int dm_mamba1_scan_phase(const dm_mamba1_args* args, int phase, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Mamba-2 forward: split [z | x | B | C | dt] -> causal conv1d + SiLU over [x|B|C] -> softplus(dt + bias)
  * -> SSD state recurrence S_t = exp(dt A_h) S_{t-1} + dt x_t (x) B_t,  y_t = S_t C_t + D_h x_t
