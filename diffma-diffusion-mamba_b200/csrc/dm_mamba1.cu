@@ -30,8 +30,7 @@ constexpr int kE = 64;        // dt_rank + 2*d_state handled by this build (R = 
 constexpr int kR = 32;
 constexpr int kTP = 32;       // tokens per conv/x_proj tile
 constexpr int kPThreads = 256;
-constexpr int kCH = 16;       // tokens per scan chunk
-constexpr int kSWarps = 2;    // warps per scan CTA
+constexpr int kCH = 8;        // tokens per scan chunk
 
 struct M1G {
     const void* xz;
@@ -241,101 +240,216 @@ __global__ void __launch_bounds__(kPThreads) m1_conv_xproj_kernel(const __grid_c
             float4 t = *reinterpret_cast<const float4*>(red + w8 * kTP * kE + o);
             s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
         }
-        *reinterpret_cast<float4*>(xd_out + static_cast<int64_t>(j0) * kE + o) = s;
+        float* dst = xd_out + static_cast<int64_t>(j0) * kE + o;
+        const int col = o % kE;
+        if (col < kR) {            // dt_low: 32 values -> [hi: 32 bf16 | lo: 32 bf16] in the first 32 float slots
+            uint32_t h0, l0, h1, l1;
+            split_bf16(s.x, s.y, h0, l0);
+            split_bf16(s.z, s.w, h1, l1);
+            uint32_t* rowp = reinterpret_cast<uint32_t*>(dst - col);
+            *reinterpret_cast<uint2*>(rowp + col / 2) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(rowp + 16 + col / 2) = make_uint2(l0, l1);
+        } else {
+            *reinterpret_cast<float4*>(dst) = s;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // Kernel S: dt_proj + softplus + selective scan + D skip + SiLU(z) gate
 // ------------------------------------------------------------------------------------------------------
+// x_dbl row (256 B, written by kernel P): [dt_low hi: 32 bf16 | dt_low lo: 32 bf16 | B: 16 f32 | C: 16 f32]
+// (dt_low = hi + lo to ~16 mantissa bits; the pair feeds the dt_proj MMA without any conversion here).
+//
+// One WARP per (sequence, 64 channels); lane owns channels c0+lane and c0+32+lane, 2 x 16 states in registers
+// as packed fp32 pairs.  Two channels per lane halve the shared-memory (MIO) traffic for B/C per MUFU op and
+// give 32 independent ex2 per token, so ~10 resident warps per SM already saturate the MUFU pipe; at the
+// BASELINE shape (1536 warp-units) every unit is resident in a single wave on 148 SMs.
+constexpr int kSC = 64;       // channels per scan warp
 template <typename T> struct ScanSmem {
-    float xd[2][kCH][kE];        // x_dbl chunk: [dt_low 32 | B 16 | C 16]
-    T us[2][kCH][32];
-    T zs[2][kCH][32];
-    float ds[kCH][33];           // delta_raw tile (token, channel-in-warp)
-    int rows[2][kCH];            // source / output row of each scanned token
+    float xd[2][kCH][kE];                    // x_dbl chunk, rows as above
+    T us[2][kCH][kSC];
+    T zs[2][kCH][kSC];
+    float ds[kCH][kSC + 4];                  // delta_raw tile (token, channel-in-warp)
+    int rows[2][kCH];                        // byte offset of each scanned token's output row
+    __nv_bfloat16 wdt[sizeof(T) == 4 ? 2 : 1][kSC][kR + 8];   // W_dt slice (hi [, lo]); 80-byte rows: ldmatrix conflict-free
 };
 
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2): halves the issue slots of the recurrence
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// softplus with torch's threshold (identity above 20).  e = exp(x); for e >= 2^-7 log(1+e) through MUFU.LG2
+// (1+e rounds with relative error <= 6e-8/e <= 8e-6), below that the series e - e^2/2 + e^3/3 (error < 2e-7).
+__device__ __forceinline__ float softplus_fast(float x) {
+    const float e = ex2_approx(x * kLog2e);
+    const float big = lg2_approx(1.0f + e) * 0.6931471805599453f;
+    const float small = e * fmaf(e, fmaf(e, 0.33333333f, -0.5f), 1.0f);
+    const float r = e < 0.0078125f ? small : big;
+    return x > 20.0f ? x : r;
+}
+__device__ __forceinline__ void ldmatrix_x4_u(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+
 template <typename T>
-__global__ void __launch_bounds__(kSWarps * 32) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
+__global__ void __launch_bounds__(32, 12) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
     constexpr bool kSplit = sizeof(T) == 4;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int unit = blockIdx.x * kSWarps + warp;
+    const int lane = threadIdx.x;
+    const int unit = blockIdx.x;
     if (unit >= n_units) return;
-    ScanSmem<T>& S = reinterpret_cast<ScanSmem<T>*>(smem_raw)[warp];
+    ScanSmem<T>& S = *reinterpret_cast<ScanSmem<T>*>(smem_raw);
 
     const int D = p.D, L = p.L;
-    const int slices = D >> 5;
+    const int slices = D / kSC;
     const int cs = unit % slices, seq = unit / slices;
     const int k = seq % p.K, b = (seq / p.K) % p.B, g = seq / (p.K * p.B);
     const M1G& G = p.g[g];
-    const int c0 = cs * 32, c = c0 + lane;
+    const int c0 = cs * kSC;
     const int32_t* ord = dir_order(p, k);
     const int64_t seq_in_group = static_cast<int64_t>(b) * p.K + k;
     const T* u_seq = static_cast<const T*>(G.u) + seq_in_group * L * D + c0;
     const T* z_base = static_cast<const T*>(G.xz) + static_cast<int64_t>(b) * G.xz_bs + D + c0;
     const float* xd_seq = G.x_dbl + seq_in_group * L * kE;
-    T* out_base = static_cast<T*>(G.out) + static_cast<int64_t>(b) * G.out_bs + static_cast<int64_t>(k) * G.out_ds + c;
+    char* out_lane = reinterpret_cast<char*>(static_cast<T*>(G.out) + static_cast<int64_t>(b) * G.out_bs +
+                                             static_cast<int64_t>(k) * G.out_ds + c0 + lane);
+    const bool token_order = p.out_order == DM_OUT_TOKEN_ORDER;
+    const int out_ts32 = static_cast<int>(G.out_ts * sizeof(T));
 
-    // per-channel constants
-    float A2[kN];
-#pragma unroll
-    for (int n = 0; n < kN; n += 4) {
-        float4 t = __ldg(reinterpret_cast<const float4*>(G.A + static_cast<int64_t>(c) * kN + n));
-        A2[n] = t.x * kLog2e; A2[n + 1] = t.y * kLog2e; A2[n + 2] = t.z * kLog2e; A2[n + 3] = t.w * kLog2e;
-    }
-    const float dtb = G.dt_bias ? __ldg(G.dt_bias + c) : 0.f;
-    const float Dc = G.D ? __ldg(G.D + c) : 0.f;
-
-    // W_dt fragments (B operand, "col" layout): n = channel c0 + nt*8 + lane/4, k = ks*16 + 2*(lane%4) (+8)
-    uint32_t bw_hi[4][2][2], bw_lo[4][2][2];
+    // ---- W_dt slice -> shared (bf16 hi [, lo]) ----
     {
-        const T* Wdt = static_cast<const T*>(G.wdt);
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const T* wp = Wdt + static_cast<int64_t>(c0 + nt * 8 + (lane >> 2)) * kR + ks * 16 + 2 * (lane & 3);
-                if constexpr (kSplit) {
-                    float2 w0 = __ldg(reinterpret_cast<const float2*>(wp));
-                    float2 w1 = __ldg(reinterpret_cast<const float2*>(wp + 8));
-                    split_bf16(w0.x, w0.y, bw_hi[nt][ks][0], bw_lo[nt][ks][0]);
-                    split_bf16(w1.x, w1.y, bw_hi[nt][ks][1], bw_lo[nt][ks][1]);
-                } else {
-                    bw_hi[nt][ks][0] = __ldg(reinterpret_cast<const uint32_t*>(wp));
-                    bw_hi[nt][ks][1] = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
-                }
+        const T* Wdt = static_cast<const T*>(G.wdt) + static_cast<int64_t>(c0) * kR;
+        for (int i = lane; i < kSC * kR / 2; i += 32) {
+            const int row = i / (kR / 2), col = (i % (kR / 2)) * 2;
+            uint32_t hi, lo = 0;
+            if constexpr (kSplit) {
+                const float2 w = __ldg(reinterpret_cast<const float2*>(Wdt + row * kR + col));
+                split_bf16(w.x, w.y, hi, lo);
+                *reinterpret_cast<uint32_t*>(&S.wdt[kSplit ? 1 : 0][row][col]) = lo;
+            } else {
+                hi = __ldg(reinterpret_cast<const uint32_t*>(Wdt + row * kR + col));
             }
+            *reinterpret_cast<uint32_t*>(&S.wdt[0][row][col]) = hi;
+        }
     }
 
-    constexpr int kSegU = 32 * sizeof(T) / 16;       // 16-byte segments per (token, 32 channels) row
+    // per-channel constants: A*log2(e) as 8 packed pairs per channel
+    uint64_t A2[2][kN / 2];
+    float dtb[2], Dc[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const int c = c0 + ch * 32 + lane;
+#pragma unroll
+        for (int n = 0; n < kN; n += 4) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(G.A + static_cast<int64_t>(c) * kN + n));
+            A2[ch][n / 2] = pack2(t.x * kLog2e, t.y * kLog2e);
+            A2[ch][n / 2 + 1] = pack2(t.z * kLog2e, t.w * kLog2e);
+        }
+        dtb[ch] = G.dt_bias ? __ldg(G.dt_bias + c) : 0.f;
+        Dc[ch] = G.D ? __ldg(G.D + c) : 0.f;
+    }
+
+    // ---- staging of one chunk (cp.async, double buffered).  Rows past the end of the sequence are clamped to
+    //      the last valid row, so the tail chunk needs no predicates (the duplicates are never consumed). ----
+    constexpr int kSegU = kSC * sizeof(T) / 16;       // 16-byte segments per (token, 64 channels) row: 8 / 16
     auto prefetch = [&](int ci) {
         const int buf = ci & 1, j0 = ci * kCH;
-        const int nrows = min(kCH, L - j0);
-        // x_dbl rows are contiguous
-        const char* xsrc = reinterpret_cast<const char*>(xd_seq + static_cast<int64_t>(j0) * kE);
-        const uint32_t xdst = smem_u32(&S.xd[buf][0][0]);
-        for (int s = lane; s < nrows * (kE * 4 / 16); s += 32) cp_async16(xdst + s * 16, xsrc + s * 16);
+        {
+            const uint32_t xdst = smem_u32(&S.xd[buf][0][0]) + lane * 16;
+            const int part = lane & 15;
+#pragma unroll
+            for (int i = 0; i < kCH / 2; ++i) {
+                const int j = min(j0 + (lane >> 4) + 2 * i, L - 1);
+                cp_async16(xdst + i * 512, reinterpret_cast<const char*>(xd_seq + static_cast<int64_t>(j) * kE) + part * 16);
+            }
+        }
         const uint32_t udst = smem_u32(&S.us[buf][0][0]), zdst = smem_u32(&S.zs[buf][0][0]);
-        for (int s = lane; s < nrows * kSegU; s += 32) {
-            const int r = s / kSegU, part = s - r * kSegU;
-            const int j = j0 + r;
+#pragma unroll
+        for (int i = 0; i < kSegU * kCH / 32; ++i) {
+            const int s = lane + 32 * i;
+            const int r = s / kSegU, part = s % kSegU;
+            const int j = min(j0 + r, L - 1);
             const int src = ord ? __ldg(ord + j) : j;
-            if (part == 0) S.rows[buf][r] = src;
+            if (part == 0) S.rows[buf][r] = (token_order ? src : j) * out_ts32;
             cp_async16(udst + s * 16, reinterpret_cast<const char*>(u_seq + static_cast<int64_t>(j) * D) + part * 16);
-            cp_async16(zdst + s * 16,
-                       reinterpret_cast<const char*>(z_base + static_cast<int64_t>(src) * G.xz_ts) + part * 16);
+            cp_async16(zdst + s * 16, reinterpret_cast<const char*>(z_base + static_cast<int64_t>(src) * G.xz_ts) + part * 16);
         }
         cp_async_commit();
     };
 
-    float h[kN];
+    uint64_t h[2][kN / 2];
 #pragma unroll
-    for (int n = 0; n < kN; ++n) h[n] = 0.f;
+    for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+        for (int n = 0; n < kN / 2; ++n) h[ch][n] = 0ull;      // bit pattern of (0.f, 0.f)
+
+    // one token of the recurrence for both channels of the lane
+    auto token = [&](int buf, int jj, float dt0, float dt1) {
+        const float dtv[2] = {dt0, dt1};
+        const ulonglong2* bc = reinterpret_cast<const ulonglong2*>(&S.xd[buf][jj][kR]);
+        ulonglong2 Bq[4], Cq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { Bq[q] = bc[q]; Cq[q] = bc[4 + q]; }
+        const int row_off = S.rows[buf][jj];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const float uu = to_f32<T>(S.us[buf][jj][ch * 32 + lane]);
+            const float zz = to_f32<T>(S.zs[buf][jj][ch * 32 + lane]);
+            const float dt = dtv[ch], dtu = dt * uu;
+            const uint64_t dt2 = pack2(dt, dt), dtu2 = pack2(dtu, dtu);
+            uint64_t y0 = 0ull, y1 = 0ull;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                {
+                    float a0, a1;
+                    unpack2(mul2(dt2, A2[ch][2 * q]), a0, a1);
+                    const uint64_t dA = pack2(ex2_approx(a0), ex2_approx(a1));
+                    h[ch][2 * q] = fma2(dA, h[ch][2 * q], mul2(dtu2, Bq[q].x));
+                    y0 = fma2(h[ch][2 * q], Cq[q].x, y0);
+                }
+                {
+                    float a0, a1;
+                    unpack2(mul2(dt2, A2[ch][2 * q + 1]), a0, a1);
+                    const uint64_t dA = pack2(ex2_approx(a0), ex2_approx(a1));
+                    h[ch][2 * q + 1] = fma2(dA, h[ch][2 * q + 1], mul2(dtu2, Bq[q].y));
+                    y1 = fma2(h[ch][2 * q + 1], Cq[q].y, y1);
+                }
+            }
+            float ya, yb, yc, yd;
+            unpack2(y0, ya, yb);
+            unpack2(y1, yc, yd);
+            const float y = fmaf(Dc[ch], uu, (ya + yb) + (yc + yd));
+            const float o = y * silu_fast(zz);
+            *reinterpret_cast<T*>(out_lane + row_off + ch * 32 * static_cast<int>(sizeof(T))) = from_f32<T>(o);
+        }
+    };
 
     const int n_chunks = (L + kCH - 1) / kCH;
     prefetch(0);
+    __syncwarp();                                    // W_dt slice visible to every lane
     for (int ci = 0; ci < n_chunks; ++ci) {
         const int buf = ci & 1, j0 = ci * kCH;
         if (ci + 1 < n_chunks) {
@@ -346,69 +460,53 @@ __global__ void __launch_bounds__(kSWarps * 32) m1_scan_kernel(const __grid_cons
         }
         __syncwarp();
 
-        // ---- delta_raw tile (16 tokens x 32 channels) = dt_low (16 x 32) . W_dt^T on mma.sync ----
+        // ---- delta_raw tile (8 tokens x 64 channels) = dt_low (8 x 32) . W_dt^T on mma.sync; rows 8..15 of the
+        //      m16 tile are fed zeros ----
         {
-            float dacc[4][4];
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dacc[nt][i] = 0.f;
-            const int r = lane >> 2, kq = 2 * (lane & 3);
+            const int r = lane >> 2, q = lane & 3;
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(&S.xd[buf][r][0]);   // 16 hi words, 16 lo words
+            uint32_t a_hi[2][4], a_lo[2][4];
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-                const float2 v0 = *reinterpret_cast<const float2*>(&S.xd[buf][r][ks * 16 + kq]);
-                const float2 v1 = *reinterpret_cast<const float2*>(&S.xd[buf][r + 8][ks * 16 + kq]);
-                const float2 v2 = *reinterpret_cast<const float2*>(&S.xd[buf][r][ks * 16 + kq + 8]);
-                const float2 v3 = *reinterpret_cast<const float2*>(&S.xd[buf][r + 8][ks * 16 + kq + 8]);
-                uint32_t a_hi[4], a_lo[4];
-                split_bf16(v0.x, v0.y, a_hi[0], a_lo[0]);
-                split_bf16(v1.x, v1.y, a_hi[1], a_lo[1]);
-                split_bf16(v2.x, v2.y, a_hi[2], a_lo[2]);
-                split_bf16(v3.x, v3.y, a_hi[3], a_lo[3]);
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    mma_bf16_16816(dacc[nt], a_hi, bw_hi[nt][ks][0], bw_hi[nt][ks][1]);
-                    // dt_low is always kept in fp32, so its low half is worth one extra MMA in both modes
-                    mma_bf16_16816(dacc[nt], a_lo, bw_hi[nt][ks][0], bw_hi[nt][ks][1]);
-                    if constexpr (kSplit) mma_bf16_16816(dacc[nt], a_hi, bw_lo[nt][ks][0], bw_lo[nt][ks][1]);
-                }
+                a_hi[ks][0] = row[ks * 8 + q]; a_hi[ks][1] = 0u; a_hi[ks][2] = row[ks * 8 + 4 + q]; a_hi[ks][3] = 0u;
+                a_lo[ks][0] = row[16 + ks * 8 + q]; a_lo[ks][1] = 0u; a_lo[ks][2] = row[16 + ks * 8 + 4 + q]; a_lo[ks][3] = 0u;
             }
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                S.ds[r][nt * 8 + kq] = dacc[nt][0];
-                S.ds[r][nt * 8 + kq + 1] = dacc[nt][1];
-                S.ds[r + 8][nt * 8 + kq] = dacc[nt][2];
-                S.ds[r + 8][nt * 8 + kq + 1] = dacc[nt][3];
+            for (int nt = 0; nt < kSC / 8; ++nt) {
+                float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+                uint32_t bw[4];
+                ldmatrix_x4_u(bw, smem_u32(&S.wdt[0][nt * 8 + (lane & 7)][(lane >> 3) * 8]));
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    mma_bf16_16816(dacc, a_hi[ks], bw[2 * ks], bw[2 * ks + 1]);
+                    mma_bf16_16816(dacc, a_lo[ks], bw[2 * ks], bw[2 * ks + 1]);
+                }
+                if constexpr (kSplit) {
+                    ldmatrix_x4_u(bw, smem_u32(&S.wdt[kSplit ? 1 : 0][nt * 8 + (lane & 7)][(lane >> 3) * 8]));
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) mma_bf16_16816(dacc, a_hi[ks], bw[2 * ks], bw[2 * ks + 1]);
+                }
+                *reinterpret_cast<float2*>(&S.ds[r][nt * 8 + 2 * q]) = make_float2(dacc[0], dacc[1]);
             }
         }
         __syncwarp();
 
-        // ---- sequential recurrence over the chunk's tokens; lane = channel ----
-        const int nrows = min(kCH, L - j0);
-#pragma unroll 2
-        for (int jj = 0; jj < nrows; ++jj) {
-            const float dt = softplus_f(S.ds[jj][lane] + dtb);
-            const float uu = to_f32<T>(S.us[buf][jj][lane]);
-            const float zz = to_f32<T>(S.zs[buf][jj][lane]);
-            const float dtu = dt * uu;
-            const float4* bc = reinterpret_cast<const float4*>(&S.xd[buf][jj][kR]);
-            float y = 0.f;
+        if (j0 + kCH <= L) {
+            // full chunk: softplus for all 8 tokens first (16 independent MUFU chains, off the recurrence's
+            // critical path), then straight-line recurrence without predicates
+            float dtv[kCH][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 Bq = bc[q], Cq = bc[4 + q];
-                const float Bv[4] = {Bq.x, Bq.y, Bq.z, Bq.w}, Cv[4] = {Cq.x, Cq.y, Cq.z, Cq.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int n = q * 4 + i;
-                    const float dA = ex2_approx(dt * A2[n]);
-                    h[n] = fmaf(dA, h[n], dtu * Bv[i]);
-                    y = fmaf(h[n], Cv[i], y);
-                }
+            for (int jj = 0; jj < kCH; ++jj) {
+                dtv[jj][0] = softplus_fast(S.ds[jj][lane] + dtb[0]);
+                dtv[jj][1] = softplus_fast(S.ds[jj][32 + lane] + dtb[1]);
             }
-            y = fmaf(Dc, uu, y);
-            const float o = y * silu_fast(zz);
-            const int row = (p.out_order == DM_OUT_TOKEN_ORDER) ? S.rows[buf][jj] : (j0 + jj);
-            out_base[static_cast<int64_t>(row) * G.out_ts] = from_f32<T>(o);
+#pragma unroll
+            for (int jj = 0; jj < kCH; ++jj) token(buf, jj, dtv[jj][0], dtv[jj][1]);
+        } else {
+            const int nrows = L - j0;
+#pragma unroll 1
+            for (int jj = 0; jj < nrows; ++jj)
+                token(buf, jj, softplus_fast(S.ds[jj][lane] + dtb[0]), softplus_fast(S.ds[jj][32 + lane] + dtb[1]));
         }
         __syncwarp();
     }
@@ -434,15 +532,16 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream) {
     }
     // kernel S
     if (phases & 2) {
-        const int n_units = n_seq * (p.D / 32);
-        const size_t bytes = sizeof(ScanSmem<T>) * kSWarps;
+        const int n_units = n_seq * (p.D / kSC);
+        const size_t bytes = sizeof(ScanSmem<T>);
         static thread_local bool configured = false;
         if (!configured) {
             DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(bytes)));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             configured = true;
         }
-        m1_scan_kernel<T><<<(n_units + kSWarps - 1) / kSWarps, kSWarps * 32, bytes, stream>>>(p, n_units);
+        m1_scan_kernel<T><<<n_units, 32, bytes, stream>>>(p, n_units);
         DM_CUDA_TRY(cudaGetLastError());
     }
     return DM_OK;
