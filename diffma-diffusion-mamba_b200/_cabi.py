@@ -15,7 +15,8 @@ DM_F32, DM_BF16 = 0, 1
 DM_MAX_GROUPS = 4
 DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
-EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba2_ssd_fwd", "dm_version", "dm_status_string", "dm_last_cuda_error",
+EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
+           "dm_spiral_post_mix", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
 
@@ -90,6 +91,13 @@ def lib() -> C.CDLL:
     L.dm_mamba1_scan_phase.argtypes = [C.POINTER(Mamba1Args), C.c_int, C.c_void_p]
     L.dm_mamba2_ssd_fwd.restype = C.c_int
     L.dm_mamba2_ssd_fwd.argtypes = [C.POINTER(Mamba2Args), C.c_void_p]
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    L.dm_spiral_pre.restype = C.c_int
+    L.dm_spiral_pre.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, f32, i32, vp]
+    L.dm_spiral_post_ln.restype = C.c_int
+    L.dm_spiral_post_ln.argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, vp]
+    L.dm_spiral_post_mix.restype = C.c_int
+    L.dm_spiral_post_mix.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, vp]
     if L.dm_version() != DM_ABI_VERSION:
         raise RuntimeError(f"diffma_b200: library ABI {L.dm_version()} != binding ABI {DM_ABI_VERSION}; rebuild")
     _LIB = L

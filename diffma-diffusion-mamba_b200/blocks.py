@@ -46,13 +46,80 @@ class Spiral_MambaBlock(nn.Module):
         self.sigmoid = nn.Sigmoid()
         self.initialize_weights()
 
-    def forward(self, x, c, w):
+    def forward(self, x, c, w, skip=None):
+        """``skip`` (optional, not in the reference signature): the long-skip tensor model.py:290-292 adds to the
+        block input; passing it here lets the fused prologue / epilogue do the add."""
+        if (not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 512
+                and x.is_contiguous()):
+            return self._forward_fused(x, c, w, skip)
+        if skip is not None:
+            x = x + skip
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
         x_ssm = modulate(self.norm1(x), shift, scale)
         w_ssm = x_ssm * w
         a, b = mix_groups([self.mamba1, self.mamba2], [x_ssm, w_ssm], "spiral")
         alpha = self.attention_network(torch.cat([a, b], dim=-1))
         return x + gate.unsqueeze(1) * (alpha * a + (1 - alpha) * b)
+
+    # ---- inference path: 8 launches per block (reference: ~100), weights cached in the act dtype ----------
+    def _fused_weights(self, act):
+        m1, m2 = self.mamba1, self.mamba2
+        params = [m1.in_proj.weight, m2.in_proj.weight, m1.out_proj.weight, m2.out_proj.weight,
+                  self.adaLN_modulation[1].weight, self.adaLN_modulation[1].bias, self.attention_network[1].weight,
+                  self.attention_network[1].bias, self.attention_network[3].weight, self.attention_network[3].bias]
+        key = (act, params[0].device, tuple(p._version for p in params))
+        cache = getattr(self, "_fcache", None)
+        if cache is not None and cache["key"] == key:
+            return cache
+        K = 3
+        cache = {
+            "key": key,
+            "w_in": torch.stack([m1.in_proj.weight, m2.in_proj.weight]).to(act).transpose(1, 2).contiguous(),
+            "w_out": torch.stack([m1.out_proj.weight.repeat(1, K), m2.out_proj.weight.repeat(1, K)]).to(act)
+                          .transpose(1, 2).contiguous(),
+            "w_out1": torch.stack([m1.out_proj.weight, m2.out_proj.weight]).to(act).transpose(1, 2).contiguous(),
+            "ada_w": self.adaLN_modulation[1].weight.to(act).contiguous(),
+            "ada_b": self.adaLN_modulation[1].bias.to(act).contiguous(),
+            "att_w": self.attention_network[1].weight.to(act).contiguous(),
+            "att_b": self.attention_network[1].bias.to(act).contiguous(),
+            "w3": self.attention_network[3].weight.detach().float().reshape(-1).contiguous(),
+            "b3": self.attention_network[3].bias.detach().float().reshape(-1).contiguous(),
+            "ln1": (self.norm1.weight.detach().float().contiguous(), self.norm1.bias.detach().float().contiguous()),
+            "ln2": (self.attention_network[0].weight.detach().float().contiguous(),
+                    self.attention_network[0].bias.detach().float().contiguous()),
+        }
+        self._fcache = cache
+        return cache
+
+    def _forward_fused(self, x, c, w, skip=None, mod=None):
+        from . import ops
+        from .mixer import Mamba2, _act_dtype
+        B, L, D = x.shape
+        act = _act_dtype(x)
+        W = self._fused_weights(act)
+        m1, m2 = self.mamba1, self.mamba2
+        is_m2 = isinstance(m1, Mamba2)
+        with torch.autocast("cuda", enabled=False):
+            if mod is None:
+                mod = F.linear(F.silu(c.float()).to(act), W["ada_w"], W["ada_b"]).float()       # (B, 3D)
+            wrow = None if w is None else w.reshape(B * L).float().contiguous()
+            x2 = ops.spiral_pre(x, skip, W["ln1"][0], W["ln1"][1], mod, wrow, act)            # (2, B*L, D)
+            proj = torch.bmm(x2, W["w_in"])                                                      # (2, B*L, d_in_proj)
+            plan = m1.plan("spiral", L, x.device)
+            xs = [proj[0].view(B, L, -1), proj[1].view(B, L, -1)]
+            if not is_m2:
+                y = ops.mamba1_scan(xs, [m1.scan_weights(act), m2.scan_weights(act)], plan)      # (2, B, L, K, d_inner)
+                ab = torch.bmm(y.view(2, B * L, -1), W["w_out"])                                 # (2, B*L, D)
+            else:
+                v, ss = ops.mamba2_ssd(xs, [m1.scan_weights(), m2.scan_weights()], plan, m1.d_inner, m1.d_state,
+                                       m1.nheads, gate=True, want_sumsq=True)                     # (2,B,L,K,d), (2,B,K,L)
+                rstd = torch.rsqrt(ss / m1.d_inner + m1.norm.eps).transpose(2, 3).unsqueeze(-1)  # (2, B, L, K, 1)
+                nw = torch.stack([m1.norm.weight, m2.norm.weight]).float().view(2, 1, 1, 1, -1)
+                vn = (v.float() * rstd * nw).to(act)
+                ab = torch.bmm(vn.view(2, B * L, -1), W["w_out"])
+            lnab = ops.spiral_post_ln(ab, W["ln2"][0], W["ln2"][1])                              # (B*L, 2D)
+            hidden = F.linear(lnab, W["att_w"], W["att_b"])                                      # (B*L, D)
+            return ops.spiral_post_mix(x, skip, ab, hidden, W["w3"], W["b3"], mod)
 
     def initialize_weights(self):
         self.apply(_basic_init)

@@ -1,0 +1,269 @@
+// Row-wise glue of Spiral_MambaBlock.forward (reference block/mamba_block.py:100-115)
+// fused into three HBM-bound kernels, one warp per token row, everything vectorised 16 B:
+//
+//   pre      x (+ long-skip) -> LayerNorm -> adaLN modulate -> [x_ssm ; x_ssm * w] in the act dtype, laid out as the
+//            (2, rows, D) operand of the batched in-projection            (reference lines 101-105 + model.py:290-292)
+//   post_ln  LayerNorm(cat(a, b)) -> act dtype, the operand of attention_network's first Linear   (line 110-111)
+//   post_mix alpha = sigmoid(w3 . silu(hidden) + b3) ; x_new = (x + skip) + gate * (alpha a + (1-alpha) b)
+//                                                                              (lines 111-114)
+// The reference runs ~35 elementwise / reduction launches for the same work.
+#include "dm_common.cuh"
+
+namespace dm {
+namespace {
+
+constexpr int kRowWarps = 4;      // rows (warps) per CTA
+
+template <typename T> struct V8;  // 8 consecutive elements <-> float[8]
+template <> struct V8<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+template <> struct V8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// D = 8 * 32 * NV elements per row; lane owns NV groups of 8 consecutive elements: element (i*32 + lane)*8 + e
+template <typename T, int NV>
+__global__ void __launch_bounds__(kRowWarps * 32)
+spiral_pre_kernel(const float* __restrict__ x, const float* __restrict__ skip, const float* __restrict__ ln_w,
+                  const float* __restrict__ ln_b, const float* __restrict__ mod, int64_t mod_stride,
+                  const float* __restrict__ w, T* __restrict__ out2, int rows, int L, float eps) {
+    constexpr int D = NV * 256;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int b = row / L;
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int64_t off = static_cast<int64_t>(row) * D + (i * 32 + lane) * 8;
+        V8<float>::load(x + off, v[i]);
+        if (skip) {
+            float t[8];
+            V8<float>::load(skip + off, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[i][e] += t[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[i][e];
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float d = v[i][e] - mean;
+            q = fmaf(d, d, q);
+        }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    const float wr = w ? __ldg(w + row) : 1.0f;
+    const float* shift = mod + static_cast<int64_t>(b) * mod_stride;
+    const float* scale = shift + D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        float g[8], bb[8], sh[8], sc[8], o1[8], o2[8];
+        V8<float>::load(ln_w + c, g);
+        V8<float>::load(ln_b + c, bb);
+        V8<float>::load(shift + c, sh);
+        V8<float>::load(scale + c, sc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float n = fmaf((v[i][e] - mean) * rstd, g[e], bb[e]);
+            o1[e] = fmaf(n, 1.0f + sc[e], sh[e]);
+            o2[e] = o1[e] * wr;
+        }
+        V8<T>::store(out2 + static_cast<int64_t>(row) * D + c, o1);
+        V8<T>::store(out2 + (static_cast<int64_t>(rows) + row) * D + c, o2);
+    }
+}
+
+// LayerNorm over cat(a, b): row of 2*D values, a = ab[0], b = ab[1]
+template <typename T, int NV>
+__global__ void __launch_bounds__(kRowWarps * 32)
+spiral_post_ln_kernel(const T* __restrict__ ab, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                      T* __restrict__ out, int rows, float eps) {
+    constexpr int D = NV * 256;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float v[2][NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            V8<T>::load(ab + (static_cast<int64_t>(h) * rows + row) * D + (i * 32 + lane) * 8, v[h][i]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += v[h][i][e];
+        }
+    const float mean = warp_sum(s) * (0.5f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = v[h][i][e] - mean;
+                q = fmaf(d, d, q);
+            }
+    const float rstd = rsqrtf(warp_sum(q) * (0.5f / D) + eps);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = h * D + (i * 32 + lane) * 8;
+            float g[8], bb[8], o[8];
+            V8<float>::load(ln_w + c, g);
+            V8<float>::load(ln_b + c, bb);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf((v[h][i][e] - mean) * rstd, g[e], bb[e]);
+            V8<T>::store(out + static_cast<int64_t>(row) * 2 * D + c, o);
+        }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(kRowWarps * 32)
+spiral_post_mix_kernel(const float* __restrict__ x, const float* __restrict__ skip, const T* __restrict__ ab,
+                       const T* __restrict__ hidden, const float* __restrict__ w3, const float* __restrict__ b3,
+                       const float* __restrict__ mod, int64_t mod_stride, float* __restrict__ out, int rows, int L) {
+    constexpr int D = NV * 256;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int b = row / L;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        float hv[8], wv[8];
+        V8<T>::load(hidden + static_cast<int64_t>(row) * D + c, hv);
+        V8<float>::load(w3 + c, wv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s = fmaf(silu_fast(hv[e]), wv[e], s);
+    }
+    const float alpha = sigmoid_fast(warp_sum(s) + __ldg(b3));
+    const float* gate = mod + static_cast<int64_t>(b) * mod_stride + 2 * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        const int64_t off = static_cast<int64_t>(row) * D + c;
+        float xa[8], av[8], bv[8], gv[8], o[8];
+        V8<float>::load(x + off, xa);
+        if (skip) {
+            float t[8];
+            V8<float>::load(skip + off, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xa[e] += t[e];
+        }
+        V8<T>::load(ab + off, av);
+        V8<T>::load(ab + static_cast<int64_t>(rows) * D + off, bv);
+        V8<float>::load(gate + c, gv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(gv[e], fmaf(alpha, av[e] - bv[e], bv[e]), xa[e]);
+        V8<float>::store(out + off, o);
+    }
+}
+
+inline int row_grid(int rows) { return (rows + kRowWarps - 1) / kRowWarps; }
+
+}  // namespace
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" int dm_spiral_pre(const float* x, const float* skip, const float* ln_weight, const float* ln_bias,
+                             const float* mod, int64_t mod_batch_stride, const float* w, void* out2, int32_t batch,
+                             int32_t seqlen, int32_t d_model, float eps, int32_t act_dtype, void* stream) {
+    if (!x || !ln_weight || !ln_bias || !mod || !out2 || batch <= 0 || seqlen <= 0) return DM_ERR_INVALID_ARG;
+    if (d_model != 512) return DM_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(out2) || !aligned16(mod) || (skip && !aligned16(skip)) || (mod_batch_stride % 4))
+        return DM_ERR_INVALID_ARG;
+    const int rows = batch * seqlen;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (act_dtype == DM_BF16)
+        spiral_pre_kernel<__nv_bfloat16, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
+            x, skip, ln_weight, ln_bias, mod, mod_batch_stride, w, static_cast<__nv_bfloat16*>(out2), rows, seqlen, eps);
+    else if (act_dtype == DM_F32)
+        spiral_pre_kernel<float, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
+            x, skip, ln_weight, ln_bias, mod, mod_batch_stride, w, static_cast<float*>(out2), rows, seqlen, eps);
+    else
+        return DM_ERR_UNSUPPORTED;
+    DM_CUDA_TRY(cudaGetLastError());
+    return DM_OK;
+}
+
+extern "C" int dm_spiral_post_ln(const void* ab, const float* ln_weight, const float* ln_bias, void* out, int32_t rows,
+                                 int32_t d_model, float eps, int32_t act_dtype, void* stream) {
+    if (!ab || !ln_weight || !ln_bias || !out || rows <= 0) return DM_ERR_INVALID_ARG;
+    if (d_model != 512) return DM_ERR_UNSUPPORTED;
+    if (!aligned16(ab) || !aligned16(out)) return DM_ERR_INVALID_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (act_dtype == DM_BF16)
+        spiral_post_ln_kernel<__nv_bfloat16, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(ab), ln_weight, ln_bias, static_cast<__nv_bfloat16*>(out), rows, eps);
+    else if (act_dtype == DM_F32)
+        spiral_post_ln_kernel<float, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
+            static_cast<const float*>(ab), ln_weight, ln_bias, static_cast<float*>(out), rows, eps);
+    else
+        return DM_ERR_UNSUPPORTED;
+    DM_CUDA_TRY(cudaGetLastError());
+    return DM_OK;
+}
+
+extern "C" int dm_spiral_post_mix(const float* x, const float* skip, const void* ab, const void* hidden,
+                                  const float* w3, const float* b3, const float* mod, int64_t mod_batch_stride, float* out,
+                                  int32_t batch, int32_t seqlen, int32_t d_model, int32_t act_dtype, void* stream) {
+    if (!x || !ab || !hidden || !w3 || !b3 || !mod || !out || batch <= 0 || seqlen <= 0) return DM_ERR_INVALID_ARG;
+    if (d_model != 512) return DM_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(ab) || !aligned16(hidden) || !aligned16(out) || !aligned16(mod) ||
+        (skip && !aligned16(skip)) || (mod_batch_stride % 4))
+        return DM_ERR_INVALID_ARG;
+    const int rows = batch * seqlen;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (act_dtype == DM_BF16)
+        spiral_post_mix_kernel<__nv_bfloat16, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
+            x, skip, static_cast<const __nv_bfloat16*>(ab), static_cast<const __nv_bfloat16*>(hidden), w3, b3, mod,
+            mod_batch_stride, out, rows, seqlen);
+    else if (act_dtype == DM_F32)
+        spiral_post_mix_kernel<float, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
+            x, skip, static_cast<const float*>(ab), static_cast<const float*>(hidden), w3, b3, mod, mod_batch_stride,
+            out, rows, seqlen);
+    else
+        return DM_ERR_UNSUPPORTED;
+    DM_CUDA_TRY(cudaGetLastError());
+    return DM_OK;
+}

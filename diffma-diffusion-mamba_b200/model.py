@@ -157,12 +157,38 @@ class DiffMa(nn.Module):
         x = x.reshape(x.shape[0], h, w, p, p, c)
         return torch.einsum("nhwpqc->nchpwq", x).reshape(x.shape[0], c, h * p, h * p)
 
+    def _fused_mods(self, c, act):
+        """adaLN of EVERY block in one GEMM: c is the same for all blocks of a forward (reference recomputes it per
+        block, block/mamba_block.py:101).  Returns (B, depth, 3D) fp32; weights cached in the act dtype."""
+        import torch.nn.functional as F
+        ps = [p for blk in self.blocks for p in (blk.adaLN_modulation[1].weight, blk.adaLN_modulation[1].bias)]
+        key = (act, ps[0].device, tuple(p._version for p in ps))
+        cache = getattr(self, "_ada_cache", None)
+        if cache is None or cache["key"] != key:
+            cache = {"key": key,
+                     "w": torch.cat([blk.adaLN_modulation[1].weight for blk in self.blocks]).to(act).contiguous(),
+                     "b": torch.cat([blk.adaLN_modulation[1].bias for blk in self.blocks]).to(act).contiguous()}
+            self._ada_cache = cache
+        with torch.autocast("cuda", enabled=False):
+            mods = F.linear(F.silu(c.float()).to(act), cache["w"], cache["b"]).float()
+        return mods.view(c.shape[0], self.depth, -1)
+
     def forward(self, x, t, y, y2, w):
         """x (N,C,H,W), t (N,), y (N,D), y2 (N,T,D), w (N,T,1) -> (N, out_channels, H, W)  [model.py:264-301]"""
         x = self.x_embedder(x) + self.pos_embed
         t = self.t_embedder(t)
         c = torch.cat((t + y, t + torch.mean(y2, dim=1)), dim=1)
+        fused = (not torch.is_grad_enabled()) and x.is_cuda and self.block_type == "spiral" and x.shape[-1] == 512
         outs = []
+        if fused:
+            from .mixer import _act_dtype
+            x = x.float().contiguous()
+            mods = self._fused_mods(c, _act_dtype(x))
+            for i in range(self.depth):
+                skip = outs[self.depth - i - 1] if (i > self.depth / 2) else None
+                x = self.blocks[i]._forward_fused(x, c, w, skip, mods[:, i])
+                outs.append(x)
+            return self.unpatchify(self.final_layer(x, c))
         for i in range(self.depth):
             if i == 0:
                 x = self.blocks[i](x, c, w)

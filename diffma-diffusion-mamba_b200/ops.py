@@ -269,7 +269,10 @@ def mamba2_ssd_raw(zxbcdt: List[torch.Tensor], weights: List[Mamba2Weights], pla
 
 def mamba2_ssd(zxbcdt, weights, plan, d_inner, d_state, nheads, gate=True, want_sumsq=True):
     if torch.is_grad_enabled() and any(t.requires_grad for t in zxbcdt):
-        raise NotImplementedError("diffma_b200: the Mamba-2 backward kernel is not built yet (forward/sampling only)")
+        from . import autograd_ops
+        v, ss = autograd_ops.Mamba2SsdFn.apply(plan, len(zxbcdt), d_inner, d_state, nheads, gate, want_sumsq, *zxbcdt,
+                                               *autograd_ops.flatten_weights(weights))
+        return v, (ss if want_sumsq else None)
     return mamba2_ssd_raw(zxbcdt, weights, plan, d_inner, d_state, nheads, gate, want_sumsq)
 
 
@@ -415,3 +418,60 @@ class RMSNormGated(torch.nn.Module):
         if z is not None and self.norm_before_gate:
             out = out * F.silu(z.float())
         return out.to(x.dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# row-wise glue of Spiral_MambaBlock.forward (reference block/mamba_block.py:100-115)
+# --------------------------------------------------------------------------------------------------
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+        raise RuntimeError(f"{what}: expected a contiguous CUDA fp32 tensor, got {t.dtype} on {t.device}")
+    return t
+
+
+def spiral_pre(x, skip, ln_weight, ln_bias, mod, w, act_dtype) -> torch.Tensor:
+    """x (B,L,D) fp32 [+ skip] -> (2, B*L, D) act dtype: [modulate(LN(x)) ; modulate(LN(x)) * w]."""
+    B, L, D = x.shape
+    out2 = torch.empty((2, B * L, D), dtype=act_dtype, device=x.device)
+    st = _cabi.lib().dm_spiral_pre(_f32c(x, "x").data_ptr(), None if skip is None else _f32c(skip, "skip").data_ptr(),
+                                   _f32c(ln_weight, "ln_weight").data_ptr(), _f32c(ln_bias, "ln_bias").data_ptr(),
+                                   _mod2d(mod).data_ptr(), mod.stride(0),
+                                   None if w is None else _f32c(w, "w").data_ptr(), out2.data_ptr(), B, L, D, 1e-5,
+                                   _dtype_code(out2), _stream_handle(x.device))
+    _cabi.check(st, "dm_spiral_pre")
+    LAUNCH_COUNTER["kernels"] += 1
+    return out2
+
+
+def spiral_post_ln(ab, ln_weight, ln_bias) -> torch.Tensor:
+    """ab (2, rows, D) -> LayerNorm(cat(ab[0], ab[1])) (rows, 2D), same dtype."""
+    _, rows, D = ab.shape
+    out = torch.empty((rows, 2 * D), dtype=ab.dtype, device=ab.device)
+    st = _cabi.lib().dm_spiral_post_ln(ab.data_ptr(), _f32c(ln_weight, "ln_weight").data_ptr(),
+                                       _f32c(ln_bias, "ln_bias").data_ptr(), out.data_ptr(), rows, D, 1e-5,
+                                       _dtype_code(ab), _stream_handle(ab.device))
+    _cabi.check(st, "dm_spiral_post_ln")
+    LAUNCH_COUNTER["kernels"] += 1
+    return out
+
+
+def spiral_post_mix(x, skip, ab, hidden, w3, b3, mod) -> torch.Tensor:
+    """alpha = sigmoid(w3 . silu(hidden) + b3); (x + skip) + gate * (alpha*ab[0] + (1-alpha)*ab[1]) -> fp32 (B,L,D)."""
+    B, L, D = x.shape
+    out = torch.empty_like(x)
+    if not (ab.is_contiguous() and hidden.is_contiguous() and hidden.dtype == ab.dtype):
+        raise RuntimeError("spiral_post_mix: ab / hidden must be contiguous and of the same dtype")
+    st = _cabi.lib().dm_spiral_post_mix(_f32c(x, "x").data_ptr(), None if skip is None else _f32c(skip, "skip").data_ptr(),
+                                        ab.data_ptr(), hidden.data_ptr(), _f32c(w3, "w3").data_ptr(),
+                                        _f32c(b3, "b3").data_ptr(), _mod2d(mod).data_ptr(), mod.stride(0),
+                                        out.data_ptr(), B, L, D, _dtype_code(ab), _stream_handle(x.device))
+    _cabi.check(st, "dm_spiral_post_mix")
+    LAUNCH_COUNTER["kernels"] += 1
+    return out
+
+
+def _mod2d(mod: torch.Tensor) -> torch.Tensor:
+    """adaLN output (B, 3D) fp32, rows may be strided (a slice of the all-blocks GEMM), channels contiguous."""
+    if mod.dtype != torch.float32 or mod.dim() != 2 or mod.stride(1) != 1 or not mod.is_cuda or mod.stride(0) % 4:
+        raise RuntimeError("mod: expected CUDA fp32 (B, 3D) with unit channel stride and 16-byte aligned rows")
+    return mod

@@ -139,6 +139,26 @@ typedef struct {
 
 int dm_mamba2_ssd_fwd(const dm_mamba2_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Row-wise glue of Spiral_MambaBlock.forward (reference block/mamba_block.py:100-115), one warp per token row.
+ * x / skip / out are the fp32 residual stream (rows = batch*seqlen, d_model = 512 in this build);
+ * `mod` is the adaLN output (batch, 3*d_model) = [shift | scale | gate] with row stride mod_batch_stride.
+ *
+ * dm_spiral_pre      out2[0] = modulate(LayerNorm(x + skip)), out2[1] = out2[0] * w[row]   (act dtype, (2, rows, d))
+ *                    -- lines 101-105, plus the long-skip add of model.py:290-292 when skip != NULL; w may be NULL.
+ * dm_spiral_post_ln  out = LayerNorm(cat(ab[0], ab[1])) (rows, 2*d), act dtype            -- attention_network[0]
+ * dm_spiral_post_mix alpha = sigmoid(w3 . silu(hidden) + b3); out = (x + skip) + gate * (alpha*a + (1-alpha)*b)
+ *                    -- attention_network[2..4] and lines 112-114; `hidden` = attention_network[1] output (rows, d).
+ * ---------------------------------------------------------------------------------------------------- */
+int dm_spiral_pre(const float* x, const float* skip, const float* ln_weight, const float* ln_bias, const float* mod,
+                  int64_t mod_batch_stride, const float* w, void* out2, int32_t batch, int32_t seqlen,
+                  int32_t d_model, float eps, int32_t act_dtype, void* stream);
+int dm_spiral_post_ln(const void* ab, const float* ln_weight, const float* ln_bias, void* out, int32_t rows,
+                      int32_t d_model, float eps, int32_t act_dtype, void* stream);
+int dm_spiral_post_mix(const float* x, const float* skip, const void* ab, const void* hidden, const float* w3,
+                       const float* b3, const float* mod, int64_t mod_batch_stride, float* out, int32_t batch,
+                       int32_t seqlen, int32_t d_model, int32_t act_dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------ */
 int dm_version(void);                     /* DM_ABI_VERSION of the loaded library                        */
 const char* dm_status_string(int status);

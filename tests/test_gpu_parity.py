@@ -188,3 +188,23 @@ def test_errors_are_loud(dev):
         ops.mamba_inner_fn(xz.half().to(dev), p["conv_w"].to(dev), p["conv_b"].to(dev), p["x_proj"].half().to(dev),
                            p["dt_proj"].half().to(dev), p["out_proj"].half().to(dev), None, p["A"].to(dev), None, None,
                            p["D"].to(dev), delta_bias=p["dt_bias"].to(dev))
+
+
+@pytest.mark.parametrize("use_m2", [False, True])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_fused_block_path_equals_module_path(dev, use_m2, dtype):
+    """The 8-launch inference path of Spiral_MambaBlock (dm_spiral_pre / post_ln / post_mix + batched GEMMs) vs the
+    module-by-module path (the one autograd uses) on the same weights, incl. the long-skip add."""
+    from diffma_b200 import model as M, synth
+    torch.manual_seed(0)
+    net = M.DiffMa_models["DiffMa-S/2"](input_size=28, dt_rank=16, d_state=16, use_mamba2=use_m2).eval()
+    synth.fill_trained_like_(net, seed=11)
+    net = net.to(dev)
+    b = synth.synthetic_batch(2, tokens=196, seed=21, device=dev)
+    ctx = torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == "bf16")
+    with ctx:
+        fused = net(b["x"], b["t"], b["y"], b["y2"], b["w"]).float()
+        with torch.enable_grad():                      # grad mode selects the unfused module path
+            plain = net(b["x"], b["t"], b["y"], b["y2"], b["w"]).float().detach()
+    tol = dict(rtol=2e-4, atol=2e-4) if dtype == "fp32" else dict(rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(fused, plain, **tol)
