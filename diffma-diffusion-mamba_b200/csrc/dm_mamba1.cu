@@ -256,6 +256,210 @@ __global__ void __launch_bounds__(kPThreads) m1_conv_xproj_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Kernel P2 (bf16 I/O, d_inner <= 1024): persistent version of kernel P.
+//   One CTA per SM keeps W_x (64 x D bf16, 132 KB) resident in shared memory for its whole life and walks
+//   16-token tiles of the scanned sequences: cp.async-staged, double-buffered x tiles (the gather by scan order
+//   happens in the copy), conv + SiLU in place (u overwrites the x rows it no longer needs), x_proj on mma.sync
+//   with BOTH operands read by ldmatrix from shared memory (no global latency inside the MMA loop), K split over
+//   the 8 warps, partials reduced through the tile buffer.  W_x is read from L2 once per CTA (19 MB total)
+//   instead of once per tile (86 MB), and tile loads overlap the previous tile's math.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kTP2 = 16;
+constexpr int kP2Threads = 512;
+
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// silu(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU instead of two; its 2^-11 relative error is below
+// the bf16 rounding applied to u right after
+__device__ __forceinline__ float silu_tanh(float x) {
+    const float h = 0.5f * x;
+    return fmaf(h, tanh_approx(h), h);
+}
+
+template <int kD>
+__global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const __grid_constant__ M1P p, int n_tiles) {
+    using T = __nv_bfloat16;
+    static_assert(kD == 2 * kP2Threads, "one channel pair per thread");
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    constexpr int ld = kD + 8;                               // bf16 elements per shared row (16-byte odd multiple)
+    constexpr int kSegs = kD * 2 / 16;                       // 16-byte segments per row
+    constexpr int tile_elems = (kTP2 + 3) * ld;
+    T* Ws = reinterpret_cast<T*>(smem_raw);                  // [64][ld]
+    T* Xs = Ws + kE * ld;                                    // [2][kTP2 + 3][ld]
+    const int L = p.L;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_per_seq = (L + kTP2 - 1) / kTP2;
+
+    auto decode = [&](int tile, int& g, int& b, int& k, int& j0) {
+        const int seq = tile / tiles_per_seq;
+        j0 = (tile - seq * tiles_per_seq) * kTP2;
+        k = seq % p.K; b = (seq / p.K) % p.B; g = seq / (p.K * p.B);
+    };
+    auto load_tile = [&](int tile, int buf) {
+        int g, b, k, j0;
+        decode(tile, g, b, k, j0);
+        const M1G& G = p.g[g];
+        const int32_t* ord = dir_order(p, k);
+        const T* x_base = static_cast<const T*>(G.xz) + static_cast<int64_t>(b) * G.xz_bs;
+        T* dst = Xs + buf * tile_elems;
+#pragma unroll
+        for (int i = 0; i < ((kTP2 + 3) * kSegs + kP2Threads - 1) / kP2Threads; ++i) {
+            const int s = tid + i * kP2Threads;
+            const int r = s / kSegs, part = s % kSegs;
+            const int j = j0 - 3 + r;
+            if (r < kTP2 + 3) {
+                T* d = dst + r * ld + part * 8;
+                if (j < 0) {
+                    *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+                } else if (j < L) {
+                    const int src = ord ? __ldg(ord + j) : j;
+                    cp_async16(smem_u32(d), x_base + static_cast<int64_t>(src) * G.xz_ts + part * 8);
+                }
+            }
+        }
+    };
+
+    // per-group state: W_x resident in shared memory, this thread's conv taps in registers
+    int cur_group = -1;
+    float cw[2][kW], cb[2];
+    const int c = tid * 2;
+    auto load_group = [&](int g) {
+        const M1G& G = p.g[g];
+        const T* Wx = static_cast<const T*>(G.wx);
+        for (int s = tid; s < kE * kSegs; s += kP2Threads) {
+            const int r = s / kSegs, part = s % kSegs;
+            cp_async16(smem_u32(Ws + r * ld + part * 8), Wx + static_cast<int64_t>(r) * kD + part * 8);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(G.conv_w + static_cast<int64_t>(c + q) * kW));
+            cw[q][0] = t.x; cw[q][1] = t.y; cw[q][2] = t.z; cw[q][3] = t.w;
+            cb[q] = G.conv_b ? __ldg(G.conv_b + c + q) : 0.f;
+        }
+        cur_group = g;
+    };
+
+    int tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    {
+        int g, b, k, j0;
+        decode(tile, g, b, k, j0);
+        load_group(g);
+        load_tile(tile, 0);
+        cp_async_commit();
+    }
+    int buf = 0;
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        int g, b, k, j0;
+        decode(tile, g, b, k, j0);
+        const M1G& G = p.g[g];
+        const int next = tile + gridDim.x;
+        if (next < n_tiles) load_tile(next, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (g != cur_group) {               // crossed into another mixer's tiles: swap the resident weights
+            load_group(g);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+        }
+
+        // ---- conv + SiLU in place; thread owns 2 adjacent channels ----
+        T* xt = Xs + buf * tile_elems;
+        const int64_t seq_in_group = static_cast<int64_t>(b) * p.K + k;
+        {
+            T* u_out = static_cast<T*>(G.u) + (seq_in_group * L + j0) * kD + c;
+            float win[3][2];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(xt + t * ld + c);
+                win[t][0] = __low2float(v); win[t][1] = __high2float(v);
+            }
+            const int nvalid = L - j0;
+#pragma unroll
+            for (int jj = 0; jj < kTP2; ++jj) {
+                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(xt + (jj + 3) * ld + c);
+                const float xn[2] = {__low2float(v), __high2float(v)};
+                float uv[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float acc = cb[q];
+                    acc = fmaf(cw[q][0], win[0][q], acc);
+                    acc = fmaf(cw[q][1], win[1][q], acc);
+                    acc = fmaf(cw[q][2], win[2][q], acc);
+                    acc = fmaf(cw[q][3], xn[q], acc);
+                    uv[q] = silu_tanh(acc);
+                    win[0][q] = win[1][q]; win[1][q] = win[2][q]; win[2][q] = xn[q];
+                }
+                const uint32_t packed = pack_bf16(uv[0], uv[1]);
+                *reinterpret_cast<uint32_t*>(xt + jj * ld + c) = packed;
+                if (jj < nvalid) *reinterpret_cast<uint32_t*>(u_out + static_cast<int64_t>(jj) * kD) = packed;
+            }
+        }
+        __syncthreads();
+
+        // ---- x_dbl tile (16 x 64) = u tile (16 x D) . W_x^T ; warp = (K-slice of D/8 channels, half of the outputs) ----
+        const int ks = warp & 7, nh = warp >> 3;
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < kD / 8 / 32; ++kk) {
+            const int k0 = ks * (kD / 8) + kk * 32;
+            uint32_t a0[4], a1[4];
+            ldmatrix_x4(a0[0], a0[1], a0[2], a0[3], smem_u32(xt + (lane & 15) * ld + k0 + (lane >> 4) * 8));
+            ldmatrix_x4(a1[0], a1[1], a1[2], a1[3], smem_u32(xt + (lane & 15) * ld + k0 + 16 + (lane >> 4) * 8));
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                uint32_t bw[4];     // B fragments of k-steps k0 and k0+16 for 8 output rows
+                ldmatrix_x4(bw[0], bw[1], bw[2], bw[3],
+                            smem_u32(Ws + ((nh * 4 + nt) * 8 + (lane & 7)) * ld + k0 + (lane >> 3) * 8));
+                mma_bf16_16816(acc[nt], a0, bw[0], bw[1]);
+                mma_bf16_16816(acc[nt], a1, bw[2], bw[3]);
+            }
+        }
+        __syncthreads();                                   // all warps done with the u rows: reuse them as reduce buffer
+        float* red = reinterpret_cast<float*>(xt);         // [8 K-slices][16][64] fp32 = 32 KB <= tile buffer
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int row = lane >> 2, col = (nh * 4 + nt) * 8 + 2 * (lane & 3);
+            float* r = red + (ks * kTP2 + row) * kE + col;
+            *reinterpret_cast<float2*>(r) = make_float2(acc[nt][0], acc[nt][1]);
+            *reinterpret_cast<float2*>(r + 8 * kE) = make_float2(acc[nt][2], acc[nt][3]);
+        }
+        __syncthreads();
+        {
+            const int o = tid * 2;                          // 16 x 64 outputs, 2 per thread
+            const int row = o / kE, col = o % kE;
+            if (j0 + row < L) {
+                float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) {
+                    const float2 t = *reinterpret_cast<const float2*>(red + w8 * kTP2 * kE + o);
+                    s.x += t.x; s.y += t.y;
+                }
+                float* rowp = G.x_dbl + (seq_in_group * L + j0 + row) * kE;
+                if (col < kR) {
+                    uint32_t hi, lo;
+                    split_bf16(s.x, s.y, hi, lo);
+                    reinterpret_cast<uint32_t*>(rowp)[col / 2] = hi;
+                    reinterpret_cast<uint32_t*>(rowp)[16 + col / 2] = lo;
+                } else {
+                    *reinterpret_cast<float2*>(rowp + col) = s;
+                }
+            }
+        }
+        __syncthreads();                                   // reduce buffer free before the next prefetch lands in it
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Kernel S: dt_proj + softplus + selective scan + D skip + SiLU(z) gate
 // ------------------------------------------------------------------------------------------------------
 // x_dbl row (256 B, written by kernel P): [dt_low hi: 32 bf16 | dt_low lo: 32 bf16 | B: 16 f32 | C: 16 f32]
@@ -518,16 +722,32 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream) {
     const bool split = sizeof(T) == 4;
     // kernel P
     if (phases & 1) {
-        const size_t smem = static_cast<size_t>(kTP) * (p.D + 8) * 2 * (split ? 2 : 1);
-        const size_t red = static_cast<size_t>(8) * kTP * kE * 4;
-        const size_t bytes = smem > red ? smem : red;
-        static thread_local size_t configured = 0;
-        if (bytes > configured) {
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(bytes)));
-            configured = bytes;
+        const size_t ld = static_cast<size_t>(p.D) + 8;
+        const size_t bytes2 = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2;
+        if (!split && p.D == 1024) {                        // bf16, d_inner 1024: persistent kernel, W_x resident in shared memory
+            static thread_local int n_sm = 0;
+            if (n_sm == 0) {
+                int dev = 0;
+                DM_CUDA_TRY(cudaGetDevice(&dev));
+                DM_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+                DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_persistent<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 227 * 1024));
+            }
+            const int n_tiles = n_seq * ((p.L + kTP2 - 1) / kTP2);
+            const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+            m1_conv_xproj_persistent<1024><<<grid, kP2Threads, bytes2, stream>>>(p, n_tiles);
+        } else {
+            const size_t smem = static_cast<size_t>(kTP) * (p.D + 8) * 2 * (split ? 2 : 1);
+            const size_t red = static_cast<size_t>(8) * kTP * kE * 4;
+            const size_t bytes = smem > red ? smem : red;
+            static thread_local size_t configured = 0;
+            if (bytes > configured) {
+                DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(bytes)));
+                configured = bytes;
+            }
+            m1_conv_xproj_kernel<T><<<n_seq * p.tiles_per_seq, kPThreads, bytes, stream>>>(p);
         }
-        m1_conv_xproj_kernel<T><<<n_seq * p.tiles_per_seq, kPThreads, bytes, stream>>>(p);
         DM_CUDA_TRY(cudaGetLastError());
     }
     // kernel S
