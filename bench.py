@@ -198,8 +198,14 @@ def kernel_roofline(args, device, peaks):
     peak = peaks.get("hbm_gbs", 6650.0)
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)
     mufu_peak = 148 * 16 * sm_mhz * 1e6
+    traffic = None
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(f"{dom}@B{B}_L{L}")
+    except (OSError, ValueError):
+        pass
     return {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": None,
+            "frac": round(achieved / peak, 4), "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback B200_PROFILING.md",
             "launch_us": {k: round(v * 1e6, 2) for k, v in res.items()},
             "token_scans_per_launch": token_scans, "algorithmic_bytes_per_token_scan": bytes_per,
