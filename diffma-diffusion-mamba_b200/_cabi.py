@@ -15,7 +15,7 @@ DM_F32, DM_BF16 = 0, 1
 DM_MAX_GROUPS = 4
 DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
-EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
+EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_scan_bwd", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
            "dm_spiral_post_mix", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
@@ -39,6 +39,11 @@ class Mamba1Args(C.Structure):
         ("order", C.c_void_p),
         ("group", Mamba1Group * DM_MAX_GROUPS),
     ]
+
+
+class Mamba1BwdGroup(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dout", "d_xz_scan", "du", "ddelta", "d_x_dbl", "dA", "dD", "d_dt_bias",
+                                          "state_workspace", "d_conv_weight", "d_conv_bias")]
 
 
 class Mamba2Group(C.Structure):
@@ -89,6 +94,8 @@ def lib() -> C.CDLL:
     L.dm_mamba1_scan_fwd.argtypes = [C.POINTER(Mamba1Args), C.c_void_p]
     L.dm_mamba1_scan_phase.restype = C.c_int
     L.dm_mamba1_scan_phase.argtypes = [C.POINTER(Mamba1Args), C.c_int, C.c_void_p]
+    L.dm_mamba1_scan_bwd.restype = C.c_int
+    L.dm_mamba1_scan_bwd.argtypes = [C.POINTER(Mamba1Args), C.POINTER(Mamba1BwdGroup), C.c_int, C.c_void_p]
     L.dm_mamba2_ssd_fwd.restype = C.c_int
     L.dm_mamba2_ssd_fwd.argtypes = [C.POINTER(Mamba2Args), C.c_void_p]
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float

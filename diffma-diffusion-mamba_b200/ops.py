@@ -70,6 +70,7 @@ class ScanPlan:
     src_len: int
     table: Optional[torch.Tensor]
     layout: str
+    table_host: Optional[torch.Tensor] = None      # CPU copy of ``table`` (identity markers are read on the host)
 
     @property
     def out_order(self) -> int:
@@ -109,7 +110,11 @@ class ScanPlan:
                     r = torch.as_tensor(list(o), dtype=torch.int64)
                     assert r.numel() == seqlen and int(r.min()) >= 0 and int(r.max()) < src_len
                     rows.append(r.to(torch.int32))
-            table = torch.stack(rows).contiguous().to(device)
+            host = torch.stack(rows).contiguous()
+            table = host.to(device)
+            plan = ScanPlan(n_dir, seqlen, src_len, table, layout)
+            plan.table_host = host
+            return plan
         return ScanPlan(n_dir, seqlen, src_len, table, layout)
 
 
@@ -148,9 +153,10 @@ def _strides(x: torch.Tensor):
     return bs, ts
 
 
-def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan):
+def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, bufs=None):
     """Fill a ``dm_mamba1_args`` for the given groups.  Returns (args, (out, u, x_dbl)); the tensors own the memory
-    the struct points at and must outlive the launch."""
+    the struct points at and must outlive the launch.  ``bufs`` = existing (out-shaped, u, x_dbl) tensors to point at
+    instead of allocating (the backward passes dout / the saved intermediates)."""
     G = len(xz)
     assert 1 <= G <= _cabi.DM_MAX_GROUPS and len(weights) == G
     x0 = xz[0]
@@ -168,9 +174,14 @@ def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: Scan
     a.order = _ptr(plan.table)
     obs, ods, ots = plan.out_strides(D)
     # one allocation per kind so groups are adjacent (lets callers view them as a batch)
-    out_all = torch.empty((G,) + plan.out_shape(B, D), dtype=x0.dtype, device=x0.device)
-    u_all = torch.empty((G, B, plan.n_dir, plan.seqlen, D), dtype=x0.dtype, device=x0.device)
-    xd_all = torch.empty((G, B, plan.n_dir, plan.seqlen, E), dtype=torch.float32, device=x0.device)
+    if bufs is None:
+        out_all = torch.empty((G,) + plan.out_shape(B, D), dtype=x0.dtype, device=x0.device)
+        u_all = torch.empty((G, B, plan.n_dir, plan.seqlen, D), dtype=x0.dtype, device=x0.device)
+        xd_all = torch.empty((G, B, plan.n_dir, plan.seqlen, E), dtype=torch.float32, device=x0.device)
+    else:
+        out_all, u_all, xd_all = bufs
+        assert out_all.is_contiguous() and u_all.is_contiguous() and xd_all.is_contiguous()
+        assert tuple(out_all.shape) == (G,) + plan.out_shape(B, D) and out_all.dtype == x0.dtype
     for g in range(G):
         x, w = xz[g], weights[g]
         if x.shape != x0.shape or x.dtype != x0.dtype or x.stride(2) != 1:

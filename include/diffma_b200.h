@@ -105,6 +105,35 @@ int dm_mamba1_scan_fwd(const dm_mamba1_args* args, void* stream);
 int dm_mamba1_scan_phase(const dm_mamba1_args* args, int phase, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Mamba-1 backward of dm_mamba1_scan_fwd (upstream `MambaInnerFn.backward` minus the out-projection:
+ * selective_scan_cuda.bwd + causal_conv1d_cuda.causal_conv1d_bwd; reached from reference train.py:259).
+ * `args` is the forward's struct (xz, u, x_dbl as the forward wrote them, weights, order table, and the out_*
+ * strides, which here describe `dout`).  All gradient buffers are fp32, contiguous, in SCAN order; buffers marked
+ * "accumulated" must be zeroed by the caller.  The GEMM-shaped gradients (through x_proj / dt_proj) are the host's
+ * job between the two phases:
+ *   phase 1  reverse scan: needs dout; writes d_xz_scan[..., d_inner:] (dz), du (scan part), ddelta (d delta_raw),
+ *            accumulates d_x_dbl[..., dt_rank:] (dB, dC), dA, dD, d_dt_bias; uses state_workspace.
+ *   host     d_x_dbl[..., :dt_rank] = ddelta . W_dt ; dW_dt = ddelta^T . dt_low ; du += d_x_dbl . W_x ; dW_x = d_x_dbl^T . u
+ *   phase 2  conv backward: reads du (total), writes d_xz_scan[..., :d_inner] (dx), accumulates d_conv_weight / bias.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* dout;          /* gradient of `out` (act dtype), addressed with args->group[g].out_*_stride            */
+    float* d_xz_scan;          /* (B, n_dir, seqlen, 2*d_inner): [dx | dz] per scanned token                           */
+    float* du;                 /* (B, n_dir, seqlen, d_inner)                                                         */
+    float* ddelta;             /* (B, n_dir, seqlen, d_inner)                                                         */
+    float* d_x_dbl;            /* (B, n_dir, seqlen, dt_rank + 2*d_state), accumulated: [d dt_low | dB | dC]           */
+    float* dA;                 /* (d_inner, d_state), accumulated                                                     */
+    float* dD;                 /* (d_inner), accumulated, or NULL                                                     */
+    float* d_dt_bias;          /* (d_inner), accumulated, or NULL                                                     */
+    float* state_workspace;    /* (B, n_dir, ceil(seqlen/8), d_inner, d_state) scratch                                 */
+    float* d_conv_weight;      /* (d_inner, d_conv), accumulated                                                      */
+    float* d_conv_bias;        /* (d_inner), accumulated, or NULL                                                     */
+} dm_mamba1_bwd_group;
+
+int dm_mamba1_scan_bwd(const dm_mamba1_args* args, const dm_mamba1_bwd_group* grads /* [n_groups] */, int phase,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Mamba-2 forward: split [z | x | B | C | dt] -> causal conv1d + SiLU over [x|B|C] -> softplus(dt + bias)
  * -> SSD state recurrence S_t = exp(dt A_h) S_{t-1} + dt x_t (x) B_t,  y_t = S_t C_t + D_h x_t
  * -> gate v = y * silu(z), and the per-token sum of squares of v that the gated RMSNorm needs.
