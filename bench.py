@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--mamba2", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--budget-s", type=float, default=150.0, help="wall-clock budget of the --impl reference run")
     return ap.parse_args()
 
 
@@ -263,7 +264,7 @@ def cpu_oracle_rate(args, budget_s, threads=None):
 def run_reference(args, world, rank):
     if rank != 0:
         return
-    total_budget = 150.0
+    total_budget = args.budget_s
     per_step = total_budget / max(1, args.steps + args.warmup)
     step, bs, sample, threads = cpu_oracle_rate(args, per_step)
     for _ in range(args.warmup):

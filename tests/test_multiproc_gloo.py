@@ -1,0 +1,97 @@
+"""world_size-2 gloo runs on CPU: the host-side multi-process logic around the path.
+
+* sampling shards the batch with no data-path collective: the per-rank seeds differ and timing is max over ranks;
+* training is DDP: gradients of ``SpacedDiffusion.training_losses`` averaged over 2 ranks equal the single-process
+  gradient on the concatenated batch (the reference relies on exactly this, train.py:153,259);
+* ``bench.py --impl reference`` under torchrun: rank 0 alone prints, the other rank exits 0 silently.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Tiny(torch.nn.Module):
+    """Stand-in denoiser with DiffMa's call signature: (x, t, y, y2, w) -> (N, 8, H, W)."""
+
+    def __init__(self):
+        super().__init__()
+        self.c = torch.nn.Conv2d(4, 8, 3, padding=1)
+        self.t = torch.nn.Linear(1, 8)
+
+    def forward(self, x, t, y, y2, w):
+        return self.c(x) + self.t(t.float().view(-1, 1) / 1000.0).view(-1, 8, 1, 1) + y.mean(1).view(-1, 1, 1, 1)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import bench
+    from diffma_b200.diffusion import create_diffusion
+    torch.manual_seed(0)
+    net = _Tiny()
+    ddp = torch.nn.parallel.DistributedDataParallel(net)
+    d = create_diffusion("")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 4, 8, 8, generator=g)
+    noise = torch.randn(4, 4, 8, 8, generator=g)
+    y = torch.randn(4, 16, generator=g)
+    t = torch.tensor([3, 250, 600, 999])
+    sl = slice(rank * 2, rank * 2 + 2)
+    loss = d.training_losses(ddp, x[sl], t[sl], dict(y=y[sl], y2=None, w=None), noise=noise[sl])["loss"].mean()
+    loss.backward()
+    grads = [p.grad.clone() for p in net.parameters()]
+    mx = bench.max_over_ranks(float(rank + 1), world, torch.device("cpu"))
+    bench.barrier(world)
+    if rank == 0:
+        q.put(([g.numpy() for g in grads], mx))
+    dist.destroy_process_group()
+
+
+def test_ddp_gloo_gradients_equal_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    grads, mx = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert mx == 2.0                                      # timing is the max over ranks
+    sys.path.insert(0, ROOT)
+    from diffma_b200.diffusion import create_diffusion
+    torch.manual_seed(0)
+    net = _Tiny()
+    d = create_diffusion("")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 4, 8, 8, generator=g)
+    noise = torch.randn(4, 4, 8, 8, generator=g)
+    y = torch.randn(4, 16, generator=g)
+    t = torch.tensor([3, 250, 600, 999])
+    d.training_losses(net, x, t, dict(y=y, y2=None, w=None), noise=noise)["loss"].mean().backward()
+    for a, p in zip(grads, net.parameters()):
+        torch.testing.assert_close(torch.from_numpy(a), p.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90), os.path.join(ROOT, "bench.py"), "--impl", "reference",
+           "--gpus", "2", "--steps", "1", "--warmup", "0", "--model", "DiffMa-S/7", "--budget-s", "4"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["metric"] == "diffusion_step_images_per_s" and d["value"] > 0

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Training-step benchmark (BASELINE config C4): DiffMa-XL/4, synthetic brain.yaml shapes, bf16 autocast,
+fwd + bwd + DDP gradient all-reduce (NCCL over NVLink) + AdamW, one process per GPU.
+
+    python train_bench.py [--steps 10 --warmup 3 --model DiffMa-XL/4 --batch 32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+        train_bench.py --gpus 8
+
+Mirrors the reference loop train.py:225-265: t ~ U{0..999}, training_losses(model, x, t, {y, y2, w}), loss.mean().backward(),
+AdamW(lr 1e-4, wd 0), EMA update.  Weak scaling (per-GPU batch fixed, reference global batch 256 = 8 x 32).
+Prints ONE JSON line on rank 0; time = CUDA events, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--model", default="DiffMa-XL/4")
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--fp32", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", rank=rank, world_size=world)
+
+    from diffma_b200 import _cabi, create_model_and_diffusion, ops, synth
+    _cabi.lib()
+    torch.manual_seed(rank)                       # train.py:99 seeds per rank
+    net, diffusion = create_model_and_diffusion(args.model, respacing="")
+    synth.fill_trained_like_(net, seed=11)
+    net = net.to(device).train()
+    ema = None
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0, fused=True)
+    patch = int(args.model.split("/")[1])
+    L = (28 // patch) ** 2
+    b = synth.synthetic_batch(args.batch, tokens=L, seed=100 + rank, device=device)
+    kw = dict(y=b["y"], y2=b["y2"], w=b["w"])
+    g = torch.Generator(device=device).manual_seed(rank)
+
+    def step():
+        t = torch.randint(0, diffusion.num_timesteps, (args.batch,), device=device, generator=g)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not args.fp32):
+            loss = diffusion.training_losses(model, b["x"], t, kw)["loss"].mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(3, args.warmup)):
+        loss = step()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        torch.distributed.barrier()
+    n0 = ops.LAUNCH_COUNTER["kernels"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        torch.distributed.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    sec = float(t.item())
+    if rank == 0:
+        nparam = sum(p.numel() for p in net.parameters() if p.requires_grad)
+        print(json.dumps({
+            "metric": "training_images_per_s", "value": round(world * args.batch * args.steps / sec, 2), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(sec / args.steps * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "dtype": "f32" if args.fp32 else "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model} training step (fwd+bwd+{'DDP all-reduce+' if world > 1 else ''}AdamW), "
+                                   f"L={L}, per-GPU batch {args.batch}", "global_batch": world * args.batch,
+                       "grad_allreduce_mib": round(nparam * 4 / 2 ** 20, 1)},
+            "loss": round(float(loss.item()), 5), "gpu_launches": ops.LAUNCH_COUNTER["kernels"] - n0}), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
