@@ -91,6 +91,18 @@ class Spiral_MambaBlock(nn.Module):
         self._fcache = cache
         return cache
 
+    def _m2_out_weights(self, act):
+        """(2, d_inner, d_model): out_proj weight with the gated-RMSNorm weight folded in (Mamba-2 mixers)."""
+        m1, m2 = self.mamba1, self.mamba2
+        ps = [m1.out_proj.weight, m2.out_proj.weight, m1.norm.weight, m2.norm.weight]
+        key = (act, ps[0].device, tuple(p._version for p in ps))
+        c = getattr(self, "_m2cache", None)
+        if c is None or c[0] != key:
+            w = torch.stack([(m.out_proj.weight.float() * m.norm.weight.float()[None, :]) for m in (m1, m2)])
+            c = (key, w.to(act).transpose(1, 2).contiguous())
+            self._m2cache = c
+        return c[1]
+
     def _forward_fused(self, x, c, w, skip=None, mod=None):
         from . import ops
         from .mixer import Mamba2, _act_dtype
@@ -113,10 +125,13 @@ class Spiral_MambaBlock(nn.Module):
             else:
                 v, ss = ops.mamba2_ssd(xs, [m1.scan_weights(), m2.scan_weights()], plan, m1.d_inner, m1.d_state,
                                        m1.nheads, gate=True, want_sumsq=True)                     # (2,B,L,K,d), (2,B,K,L)
-                rstd = torch.rsqrt(ss / m1.d_inner + m1.norm.eps).transpose(2, 3).unsqueeze(-1)  # (2, B, L, K, 1)
-                nw = torch.stack([m1.norm.weight, m2.norm.weight]).float().view(2, 1, 1, 1, -1)
-                vn = (v.float() * rstd * nw).to(act)
-                ab = torch.bmm(vn.view(2, B * L, -1), W["w_out"])
+                # gated RMSNorm + merge + out_proj: rstd is a per-(token, direction) scalar and the norm weight a
+                # per-channel one, so  sum_k rstd_k (v_k * w_norm) W^T = sum_k rstd_k * (v_k (W * w_norm)^T):
+                # the weight is folded into W_out once (cached) and rstd applied to the 512-wide GEMM output.
+                K = plan.n_dir
+                o = torch.bmm(v.view(2, B * L * K, -1), self._m2_out_weights(act))               # (2, B*L*K, D)
+                rstd = torch.rsqrt(ss / m1.d_inner + m1.norm.eps).transpose(2, 3)                # (2, B, L, K)
+                ab = (o.view(2, B * L, K, D) * rstd.reshape(2, B * L, K, 1).to(act)).sum(2)
             lnab = ops.spiral_post_ln(ab, W["ln2"][0], W["ln2"][1])                              # (B*L, 2D)
             hidden = F.linear(lnab, W["att_w"], W["att_b"])                                      # (B*L, D)
             return ops.spiral_post_mix(x, skip, ab, hidden, W["w3"], W["b3"], mod)

@@ -18,8 +18,7 @@ namespace {
 
 constexpr int kN = 16;
 constexpr int kW = 4;
-constexpr int kCH = 16;
-constexpr int kWarps = 2;
+constexpr int kCH = 8;
 
 struct M2G {
     const void* in;
@@ -41,13 +40,15 @@ struct M2P {
     M2G g[DM_MAX_GROUPS];
 };
 
+constexpr int kSC = 64;       // channels per warp (one head when headdim = 64): lane owns channels c0+lane, c0+32+lane
+
 template <typename T> struct SsdSmem {
-    T xs[2][kCH][32];
-    T zs[2][kCH][32];
+    T xs[2][kCH][kSC];
+    T zs[2][kCH][kSC];
     T bcs[2][kCH][32];      // raw [B | C] rows of the chunk
     float bc[kCH][32];      // conv + SiLU of them
     float dt[kCH], dA[kCH];
-    int rows[2][kCH];
+    int rows[2][kCH];       // output row index of each scanned token
 };
 
 __device__ __forceinline__ const int32_t* dir_order(const M2P& p, int k) {
@@ -55,69 +56,151 @@ __device__ __forceinline__ const int32_t* dir_order(const M2P& p, int k) {
     const int32_t* o = p.order + static_cast<int64_t>(k) * p.L;
     return (__ldg(o) < 0) ? nullptr : o;
 }
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 
+// One WARP per (sequence, 64 channels inside one head); lane owns 2 channels, 2 x 16 states as packed fp32 pairs.
 template <typename T>
-__global__ void __launch_bounds__(kWarps * 32) m2_ssd_kernel(const __grid_constant__ M2P p, int n_units) {
+__global__ void __launch_bounds__(32, 12) m2_ssd_kernel(const __grid_constant__ M2P p, int n_units) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int unit = blockIdx.x * kWarps + warp;
+    const int lane = threadIdx.x;
+    const int unit = blockIdx.x;
     if (unit >= n_units) return;
-    SsdSmem<T>& S = reinterpret_cast<SsdSmem<T>*>(smem_raw)[warp];
+    SsdSmem<T>& S = *reinterpret_cast<SsdSmem<T>*>(smem_raw);
 
     const int D = p.D, L = p.L;
-    const int slices = D >> 5;
+    const int slices = D / kSC;
     const int cs = unit % slices, seq = unit / slices;
     const int k = seq % p.K, b = (seq / p.K) % p.B, g = seq / (p.K * p.B);
     const M2G& G = p.g[g];
-    const int c0 = cs * 32, c = c0 + lane, head = c0 / p.P;
+    const int c0 = cs * kSC, head = c0 / p.P;
     const int32_t* ord = dir_order(p, k);
     const T* in_base = static_cast<const T*>(G.in) + static_cast<int64_t>(b) * G.in_bs;
-    T* out_base = static_cast<T*>(G.out) + static_cast<int64_t>(b) * G.out_bs + static_cast<int64_t>(k) * G.out_ds + c;
+    T* out_base = static_cast<T*>(G.out) + static_cast<int64_t>(b) * G.out_bs + static_cast<int64_t>(k) * G.out_ds + c0 + lane;
     float* ssq = G.sumsq ? G.sumsq + static_cast<int64_t>(b) * G.ss_bs + static_cast<int64_t>(k) * G.ss_ds : nullptr;
+    const bool token_order = p.out_order == DM_OUT_TOKEN_ORDER;
 
-    // conv taps: own x channel (conv channel c) and own B|C channel (conv channel D + lane)
-    float wx[kW], wb[kW];
+    // conv taps: own two x channels and own B|C channel (conv channel D + lane)
+    float wx[2][kW], bx[2], wb[kW];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(G.conv_w + static_cast<int64_t>(c0 + ch * 32 + lane) * kW));
+        wx[ch][0] = t.x; wx[ch][1] = t.y; wx[ch][2] = t.z; wx[ch][3] = t.w;
+        bx[ch] = G.conv_b ? __ldg(G.conv_b + c0 + ch * 32 + lane) : 0.f;
+    }
     {
-        float4 t = __ldg(reinterpret_cast<const float4*>(G.conv_w + static_cast<int64_t>(c) * kW));
-        wx[0] = t.x; wx[1] = t.y; wx[2] = t.z; wx[3] = t.w;
-        t = __ldg(reinterpret_cast<const float4*>(G.conv_w + static_cast<int64_t>(D + lane) * kW));
+        const float4 t = __ldg(reinterpret_cast<const float4*>(G.conv_w + static_cast<int64_t>(D + lane) * kW));
         wb[0] = t.x; wb[1] = t.y; wb[2] = t.z; wb[3] = t.w;
     }
-    const float bx = G.conv_b ? __ldg(G.conv_b + c) : 0.f;
     const float bb = G.conv_b ? __ldg(G.conv_b + D + lane) : 0.f;
     const float A2 = __ldg(G.A + head) * kLog2e;
     const float dtb = G.dt_bias ? __ldg(G.dt_bias + head) : 0.f;
     const float Dh = G.D ? __ldg(G.D + head) : 0.f;
     const int dt_off = 2 * D + 2 * kN + head;
 
-    constexpr int kSeg = 32 * sizeof(T) / 16;
+    constexpr int kSeg = kSC * sizeof(T) / 16;      // 16-byte segments per (token, 64 channels): 8 / 16
+    constexpr int kSegB = 32 * sizeof(T) / 16;      // per (token, B|C row): 4 / 8
     float dt_next = 0.f;
     auto prefetch = [&](int ci) {
         const int buf = ci & 1, j0 = ci * kCH;
-        const int nrows = min(kCH, L - j0);
         const uint32_t xdst = smem_u32(&S.xs[buf][0][0]), zdst = smem_u32(&S.zs[buf][0][0]),
                        bdst = smem_u32(&S.bcs[buf][0][0]);
-        for (int s = lane; s < nrows * kSeg; s += 32) {
-            const int r = s / kSeg, part = s - r * kSeg;
-            const int j = j0 + r;
+#pragma unroll
+        for (int i = 0; i < kSeg * kCH / 32; ++i) {
+            const int s = lane + 32 * i;
+            const int r = s / kSeg, part = s % kSeg;
+            const int j = min(j0 + r, L - 1);
             const int src = ord ? __ldg(ord + j) : j;
-            if (part == 0) S.rows[buf][r] = src;
+            if (part == 0) S.rows[buf][r] = token_order ? src : j;
             const char* row = reinterpret_cast<const char*>(in_base + static_cast<int64_t>(src) * G.in_ts);
             cp_async16(zdst + s * 16, row + static_cast<size_t>(c0) * sizeof(T) + part * 16);
             cp_async16(xdst + s * 16, row + static_cast<size_t>(D + c0) * sizeof(T) + part * 16);
-            cp_async16(bdst + s * 16, row + static_cast<size_t>(2 * D) * sizeof(T) + part * 16);
+        }
+#pragma unroll
+        for (int i = 0; i < (kSegB * kCH + 31) / 32; ++i) {
+            const int s = lane + 32 * i;
+            const int r = s / kSegB, part = s % kSegB;
+            if (r < kCH) {
+                const int j = min(j0 + r, L - 1);
+                const int src = ord ? __ldg(ord + j) : j;
+                const char* row = reinterpret_cast<const char*>(in_base + static_cast<int64_t>(src) * G.in_ts);
+                cp_async16(bdst + s * 16, row + static_cast<size_t>(2 * D) * sizeof(T) + part * 16);
+            }
         }
         cp_async_commit();
-        if (lane < nrows) {                       // raw dt of (token j0+lane, own head): one scalar per lane
-            const int src = ord ? __ldg(ord + j0 + lane) : (j0 + lane);
+        if (lane < kCH) {                         // raw dt of (token j0+lane, own head): one scalar per lane
+            const int j = min(j0 + lane, L - 1);
+            const int src = ord ? __ldg(ord + j) : j;
             dt_next = to_f32<T>(in_base[static_cast<int64_t>(src) * G.in_ts + dt_off]);
         }
     };
 
-    float h[kN];
+    uint64_t h[2][kN / 2];
 #pragma unroll
-    for (int n = 0; n < kN; ++n) h[n] = 0.f;
-    float winx[3] = {0.f, 0.f, 0.f}, winb[3] = {0.f, 0.f, 0.f};
+    for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+        for (int n = 0; n < kN / 2; ++n) h[ch][n] = 0ull;
+    float winx[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, winb[3] = {0.f, 0.f, 0.f};
+
+    auto token = [&](int buf, int jj) {
+        const ulonglong2* bc = reinterpret_cast<const ulonglong2*>(&S.bc[jj][0]);
+        ulonglong2 Bq[4], Cq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { Bq[q] = bc[q]; Cq[q] = bc[4 + q]; }
+        const float dA = S.dA[jj], dt = S.dt[jj];
+        const uint64_t dA2 = pack2(dA, dA);
+        const int row = S.rows[buf][jj];
+        float s2 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const float xr = to_f32<T>(S.xs[buf][jj][ch * 32 + lane]);
+            float acc = bx[ch];
+            acc = fmaf(wx[ch][0], winx[ch][0], acc);
+            acc = fmaf(wx[ch][1], winx[ch][1], acc);
+            acc = fmaf(wx[ch][2], winx[ch][2], acc);
+            acc = fmaf(wx[ch][3], xr, acc);
+            const float xv = silu_fast(acc);
+            winx[ch][0] = winx[ch][1]; winx[ch][1] = winx[ch][2]; winx[ch][2] = xr;
+            const float dtx = dt * xv;
+            const uint64_t dtx2 = pack2(dtx, dtx);
+            uint64_t y0 = 0ull, y1 = 0ull;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                h[ch][2 * q] = fma2(dA2, h[ch][2 * q], mul2(dtx2, Bq[q].x));
+                y0 = fma2(h[ch][2 * q], Cq[q].x, y0);
+                h[ch][2 * q + 1] = fma2(dA2, h[ch][2 * q + 1], mul2(dtx2, Bq[q].y));
+                y1 = fma2(h[ch][2 * q + 1], Cq[q].y, y1);
+            }
+            float ya, yb, yc, yd;
+            unpack2(y0, ya, yb);
+            unpack2(y1, yc, yd);
+            float v = fmaf(Dh, xv, (ya + yb) + (yc + yd));
+            if (p.gate) v *= silu_fast(to_f32<T>(S.zs[buf][jj][ch * 32 + lane]));
+            out_base[static_cast<int64_t>(row) * G.out_ts + ch * 32] = from_f32<T>(v);
+            s2 = fmaf(v, v, s2);
+        }
+        if (ssq) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            if (lane == 0) atomicAdd(ssq + row, s2);
+        }
+    };
 
     const int n_chunks = (L + kCH - 1) / kCH;
     prefetch(0);
@@ -131,10 +214,10 @@ __global__ void __launch_bounds__(kWarps * 32) m2_ssd_kernel(const __grid_consta
             cp_async_wait<0>();
         }
         __syncwarp();
-        const int nrows = min(kCH, L - j0);
 
         // ---- per-chunk prologue: conv + SiLU of B|C (lane = B|C channel), dt / decay (lane = token) ----
-        for (int jj = 0; jj < nrows; ++jj) {
+#pragma unroll
+        for (int jj = 0; jj < kCH; ++jj) {
             const float v = to_f32<T>(S.bcs[buf][jj][lane]);
             float acc = bb;
             acc = fmaf(wb[0], winb[0], acc);
@@ -144,49 +227,20 @@ __global__ void __launch_bounds__(kWarps * 32) m2_ssd_kernel(const __grid_consta
             S.bc[jj][lane] = silu_fast(acc);
             winb[0] = winb[1]; winb[1] = winb[2]; winb[2] = v;
         }
-        if (lane < nrows) {
+        if (lane < kCH) {
             const float dt = softplus_f(dt_raw + dtb);
             S.dt[lane] = dt;
             S.dA[lane] = ex2_approx(dt * A2);
         }
         __syncwarp();
 
-        // ---- recurrence; lane = channel ----
-#pragma unroll 2
-        for (int jj = 0; jj < nrows; ++jj) {
-            const float xr = to_f32<T>(S.xs[buf][jj][lane]);
-            float acc = bx;
-            acc = fmaf(wx[0], winx[0], acc);
-            acc = fmaf(wx[1], winx[1], acc);
-            acc = fmaf(wx[2], winx[2], acc);
-            acc = fmaf(wx[3], xr, acc);
-            const float xv = silu_fast(acc);
-            winx[0] = winx[1]; winx[1] = winx[2]; winx[2] = xr;
-            const float dA = S.dA[jj], dtx = S.dt[jj] * xv;
-            const float4* bc = reinterpret_cast<const float4*>(&S.bc[jj][0]);
-            float y = 0.f;
+        if (j0 + kCH <= L) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 Bq = bc[q], Cq = bc[4 + q];
-                const float Bv[4] = {Bq.x, Bq.y, Bq.z, Bq.w}, Cv[4] = {Cq.x, Cq.y, Cq.z, Cq.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int n = q * 4 + i;
-                    h[n] = fmaf(dA, h[n], dtx * Bv[i]);
-                    y = fmaf(h[n], Cv[i], y);
-                }
-            }
-            y = fmaf(Dh, xv, y);
-            float v = y;
-            if (p.gate) v *= silu_fast(to_f32<T>(S.zs[buf][jj][lane]));
-            const int row = (p.out_order == DM_OUT_TOKEN_ORDER) ? S.rows[buf][jj] : (j0 + jj);
-            out_base[static_cast<int64_t>(row) * G.out_ts] = from_f32<T>(v);
-            if (ssq) {
-                float s2 = v * v;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                if (lane == 0) atomicAdd(ssq + row, s2);
-            }
+            for (int jj = 0; jj < kCH; ++jj) token(buf, jj);
+        } else {
+            const int nrows = L - j0;
+#pragma unroll 1
+            for (int jj = 0; jj < nrows; ++jj) token(buf, jj);
         }
         __syncwarp();
     }
@@ -194,15 +248,16 @@ __global__ void __launch_bounds__(kWarps * 32) m2_ssd_kernel(const __grid_consta
 
 template <typename T>
 int launch_m2(const M2P& p, cudaStream_t stream) {
-    const int n_units = p.n_groups * p.B * p.K * (p.D / 32);
-    const size_t bytes = sizeof(SsdSmem<T>) * kWarps;
+    const int n_units = p.n_groups * p.B * p.K * (p.D / kSC);
+    const size_t bytes = sizeof(SsdSmem<T>);
     static thread_local bool configured = false;
     if (!configured) {
         DM_CUDA_TRY(cudaFuncSetAttribute(m2_ssd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(bytes)));
+        DM_CUDA_TRY(cudaFuncSetAttribute(m2_ssd_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    m2_ssd_kernel<T><<<(n_units + kWarps - 1) / kWarps, kWarps * 32, bytes, stream>>>(p, n_units);
+    m2_ssd_kernel<T><<<n_units, 32, bytes, stream>>>(p, n_units);
     DM_CUDA_TRY(cudaGetLastError());
     return DM_OK;
 }
@@ -220,7 +275,7 @@ extern "C" int dm_mamba2_ssd_fwd(const dm_mamba2_args* a, void* stream) {
     if (a->d_state != kN || a->d_conv != kW) return DM_ERR_UNSUPPORTED;
     if (a->nheads <= 0 || a->d_inner <= 0 || a->d_inner % a->nheads != 0) return DM_ERR_INVALID_ARG;
     const int P = a->d_inner / a->nheads;
-    if (P % 32 != 0) return DM_ERR_UNSUPPORTED;
+    if (P % 64 != 0) return DM_ERR_UNSUPPORTED;      // a warp owns 64 channels of one head
     const size_t es = dtype_size(a->act_dtype);
     if ((static_cast<size_t>(2 * a->d_inner) * es) % 16 != 0) return DM_ERR_UNSUPPORTED;
     M2P p{};
