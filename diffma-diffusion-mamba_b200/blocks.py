@@ -7,11 +7,19 @@ EfficientVMamba :343-397, DiT :400-418) so checkpoints load.  The Spiral block h
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
 
 from .mixer import Mamba, Mamba2, mix_groups
+
+
+# DIFFMA_GEMM=tcgen05 routes the in/out projections of the fused block path through the hand-written tcgen05 GEMM
+# (dm_gemm_bf16_tn).  Default is the library GEMM: at these shapes cuBLAS' 256x192 2-CTA tiles move ~1.5x fewer
+# bytes from L2 than our 128x256 single-CTA tiles (14-15 us vs 20 us per projection, profiles/r01_notes.md).
+_USE_TCGEN05_GEMM = os.environ.get("DIFFMA_GEMM", "cublas") == "tcgen05"
 
 
 def modulate(x, shift, scale):
@@ -77,7 +85,8 @@ class Spiral_MambaBlock(nn.Module):
             "w_in": torch.stack([m1.in_proj.weight, m2.in_proj.weight]).to(act).transpose(1, 2).contiguous(),
             "w_out": torch.stack([m1.out_proj.weight.repeat(1, K), m2.out_proj.weight.repeat(1, K)]).to(act)
                           .transpose(1, 2).contiguous(),
-            "w_out1": torch.stack([m1.out_proj.weight, m2.out_proj.weight]).to(act).transpose(1, 2).contiguous(),
+            "w_in_nk": torch.stack([m1.in_proj.weight, m2.in_proj.weight]).to(act).contiguous(),          # (2, N, K)
+            "w_out_nk": torch.stack([m1.out_proj.weight.repeat(1, K), m2.out_proj.weight.repeat(1, K)]).to(act).contiguous(),
             "ada_w": self.adaLN_modulation[1].weight.to(act).contiguous(),
             "ada_b": self.adaLN_modulation[1].bias.to(act).contiguous(),
             "att_w": self.attention_network[1].weight.to(act).contiguous(),
@@ -116,12 +125,14 @@ class Spiral_MambaBlock(nn.Module):
                 mod = F.linear(F.silu(c.float()).to(act), W["ada_w"], W["ada_b"]).float()       # (B, 3D)
             wrow = None if w is None else w.reshape(B * L).float().contiguous()
             x2 = ops.spiral_pre(x, skip, W["ln1"][0], W["ln1"][1], mod, wrow, act)            # (2, B*L, D)
-            proj = torch.bmm(x2, W["w_in"])                                                      # (2, B*L, d_in_proj)
+            tc = act == torch.bfloat16 and _USE_TCGEN05_GEMM       # hand-written tcgen05 GEMM (dm_gemm_bf16_tn)
+            proj = ops.gemm_bf16_tn(x2, W["w_in_nk"]) if tc else torch.bmm(x2, W["w_in"])     # (2, B*L, d_in_proj)
             plan = m1.plan("spiral", L, x.device)
             xs = [proj[0].view(B, L, -1), proj[1].view(B, L, -1)]
             if not is_m2:
                 y = ops.mamba1_scan(xs, [m1.scan_weights(act), m2.scan_weights(act)], plan)      # (2, B, L, K, d_inner)
-                ab = torch.bmm(y.view(2, B * L, -1), W["w_out"])                                 # (2, B*L, D)
+                yv = y.view(2, B * L, -1)
+                ab = ops.gemm_bf16_tn(yv, W["w_out_nk"]) if tc else torch.bmm(yv, W["w_out"])  # (2, B*L, D)
             else:
                 v, ss = ops.mamba2_ssd(xs, [m1.scan_weights(), m2.scan_weights()], plan, m1.d_inner, m1.d_state,
                                        m1.nheads, gate=True, want_sumsq=True)                     # (2,B,L,K,d), (2,B,K,L)

@@ -1,0 +1,258 @@
+// Batched bf16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), hand-written for sm_100a:
+//
+//     C[g] (M x N, bf16) = rowscale[g] (.) ( A[g] (M x K, bf16, K contiguous) . B[g] (N x K, bf16, K contiguous)^T )
+//
+// This is the shape of the dense projections around the scan (SURVEY.md section 8a rows a3/a6 and the out-projection
+// of a4/a7): in_proj  A = [x_ssm ; x_ssm*w] (2, B*L, 512), B = in_proj.weight (2, 2048|2096, 512);
+//            out_proj A = un-permuted gated scan output (2, B*L, K_dir*1024), B = out_proj.weight tiled K_dir times.
+// The optional row scale is the epilogue hook for the soft-mask (x_ssm*w).W = w (.) (x_ssm.W) and the RMSNorm rstd.
+//
+// Structure (one CTA per 128 x 128 output tile, 192 threads):
+//   warp 0 / lane 0   TMA producer: cp.async.bulk.tensor (128B swizzle) of a 128x64 A tile and a 128x64 B tile per
+//                     stage into a 4-stage shared-memory ring, completion on `full[s]` mbarriers (expect_tx);
+//   warp 1 / lane 0   MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16, 4 per stage, accumulator in
+//                     TMEM (128 lanes x 128 fp32 columns); tcgen05.commit releases the stage (`empty[s]`) and finally
+//                     signals `acc_full`;
+//   warps 2..5        epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> row scale -> bf16 -> global.
+// Every mbarrier wait is bounded (trap instead of hanging the GPU if a descriptor is wrong).
+#include <cuda.h>
+#include <cstdlib>
+
+#include "dm_common.cuh"
+
+namespace dm {
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kGemmThreads = 192;
+
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 28); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+    return static_cast<uint64_t>((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate,
+                                          uint32_t kIdesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GemmParams {
+    __nv_bfloat16* C;
+    const float* row_scale;       // (G, M) or nullptr
+    int64_t c_group_stride, c_row_stride;
+    int M, N, K;
+};
+
+template <int BN, int STAGES, int MINB>
+__global__ void __launch_bounds__(kGemmThreads, MINB)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const GemmParams p) {
+    constexpr uint32_t kStageBytes = (BM + BN) * BK * 2;
+    constexpr uint32_t kTmemCols = BN;
+    constexpr uint32_t kIdesc = make_idesc(BN);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages][A 16 KB | B 16 KB] (1024-byte aligned for the 128B swizzle), then barriers + tmem slot
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aligned + STAGES * kStageBytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    const uint32_t acc_full = bar0 + 8u * (2 * STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, g = blockIdx.z;
+    const int k_tiles = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ===== TMA producer =====
+            for (int kt = 0; kt < k_tiles; ++kt) {
+                const int s = kt % STAGES, round = kt / STAGES;
+                mbar_wait_bounded(empty(s), (round & 1) ^ 1);
+                mbar_expect_tx(full(s), kStageBytes);
+                const uint32_t a_dst = smem_base + s * kStageBytes, b_dst = a_dst + BM * BK * 2;
+                tma_load_3d(a_dst, &map_a, full(s), kt * BK, m0, g);
+                tma_load_3d(b_dst, &map_b, full(s), kt * BK, n0, g);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ===== MMA issuer =====
+            for (int kt = 0; kt < k_tiles; ++kt) {
+                const int s = kt % STAGES, round = kt / STAGES;
+                mbar_wait_bounded(full(s), round & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_base + s * kStageBytes, b_addr = a_addr + BM * BK * 2;
+                const uint64_t a_desc = smem_desc_sw128(a_addr), b_desc = smem_desc_sw128(b_addr);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)          // advance 16 elements = 32 B inside the swizzle atom
+                    umma_bf16(tmem_acc, a_desc + 2 * k, b_desc + 2 * k, (kt | k) != 0, kIdesc);
+                umma_commit(empty(s));                     // stage reusable once these MMAs have read it
+            }
+            umma_commit(acc_full);                         // accumulator complete
+        }
+    } else {                                               // ===== epilogue: warps 2..5 =====
+        const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
+        mbar_wait_bounded(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + quad * 32 + lane;
+        const float rs = (p.row_scale && row < p.M) ? p.row_scale[static_cast<int64_t>(g) * p.M + row] : 1.0f;
+        __nv_bfloat16* crow = p.C + static_cast<int64_t>(g) * p.c_group_stride + static_cast<int64_t>(row) * p.c_row_stride + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
+            if (row < p.M) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (n0 + c + i < p.N) {                // N is a multiple of 8 (checked on the host)
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[i + 2 * j]) * rs,
+                                                                     __uint_as_float(v[i + 2 * j + 1]) * rs);
+                            w[j] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        *reinterpret_cast<uint4*>(crow + c + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(kTmemCols) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// (G, rows, K) bf16 row-major operand -> 3-D tensor map with a 64 x 128 box and the 128-byte swizzle
+int make_map(CUtensorMap* map, const void* base, int G, int rows, int K, int64_t group_stride, int64_t row_stride,
+             int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return DM_ERR_CUDA;
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(G)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_stride) * 2, static_cast<cuuint64_t>(group_stride) * 2};
+    const cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(box_rows), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? DM_OK : DM_ERR_INVALID_ARG;
+}
+
+}  // namespace
+}  // namespace dm
+
+extern "C" int dm_gemm_bf16_tn(const void* A, int64_t a_group_stride, int64_t a_row_stride, const void* B,
+                               int64_t b_group_stride, int64_t b_row_stride, void* C, int64_t c_group_stride,
+                               int64_t c_row_stride, const float* row_scale, int32_t groups, int32_t M, int32_t N,
+                               int32_t K, void* stream) {
+    using namespace dm;
+    if (!A || !B || !C || groups <= 0 || M <= 0 || N <= 0 || K <= 0) return DM_ERR_INVALID_ARG;
+    if (K % 8 || N % 8 || a_row_stride % 8 || b_row_stride % 8 || a_group_stride % 8 || b_group_stride % 8 || c_row_stride % 8)
+        return DM_ERR_INVALID_ARG;
+    if (!aligned16(A) || !aligned16(B) || !aligned16(C)) return DM_ERR_INVALID_ARG;
+    // tile configuration: wide N tiles when the output is wide (halves the re-reads of A), 2 CTAs per SM so one CTA's
+    // epilogue overlaps the other's main loop.  DM_GEMM_CONFIG (0..2) overrides for experiments.
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("DM_GEMM_CONFIG");
+        forced = e ? atoi(e) : -1;
+    }
+    const int cfg = forced >= 0 ? forced : (N % 256 == 0 ? 4 : 0);
+    const int bn = (cfg == 1 || cfg == 3 || cfg == 4) ? 256 : 128;
+    CUtensorMap map_a, map_b;
+    int st = make_map(&map_a, A, groups, M, K, a_group_stride, a_row_stride, BM);
+    if (st != DM_OK) return st;
+    st = make_map(&map_b, B, groups, N, K, b_group_stride, b_row_stride, bn);
+    if (st != DM_OK) return st;
+    GemmParams p{static_cast<__nv_bfloat16*>(C), row_scale, c_group_stride, c_row_stride, M, N, K};
+    dim3 grid((M + BM - 1) / BM, (N + bn - 1) / bn, groups);
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+#define DM_LAUNCH_GEMM(BN_, ST_, MB_)                                                                            \
+    do {                                                                                                         \
+        const size_t smem = ST_ * (BM + BN_) * BK * 2 + 1024 + 256;                                              \
+        static thread_local bool configured = false;                                                             \
+        if (!configured) {                                                                                       \
+            DM_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN_, ST_, MB_>,                            \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+            configured = true;                                                                                   \
+        }                                                                                                        \
+        gemm_bf16_tcgen05_kernel<BN_, ST_, MB_><<<grid, kGemmThreads, smem, cs>>>(map_a, map_b, p);              \
+    } while (0)
+    if (cfg == 1) DM_LAUNCH_GEMM(256, 2, 2);
+    else if (cfg == 3) DM_LAUNCH_GEMM(256, 4, 1);
+    else if (cfg == 4) DM_LAUNCH_GEMM(256, 3, 1);
+    else if (cfg == 2) DM_LAUNCH_GEMM(128, 4, 1);
+    else DM_LAUNCH_GEMM(128, 3, 2);
+#undef DM_LAUNCH_GEMM
+    DM_CUDA_TRY(cudaGetLastError());
+    return DM_OK;
+}

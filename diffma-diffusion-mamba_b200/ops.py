@@ -486,3 +486,29 @@ def _mod2d(mod: torch.Tensor) -> torch.Tensor:
     if mod.dtype != torch.float32 or mod.dim() != 2 or mod.stride(1) != 1 or not mod.is_cuda or mod.stride(0) % 4:
         raise RuntimeError("mod: expected CUDA fp32 (B, 3D) with unit channel stride and 16-byte aligned rows")
     return mod
+
+
+# --------------------------------------------------------------------------------------------------
+# tcgen05 GEMM
+# --------------------------------------------------------------------------------------------------
+def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[g] = row_scale[g][:, None] * (a[g] @ b[g].T) on the hand-written tcgen05 kernel.
+    a (G, M, K), b (G, N, K) bf16 with unit stride along K; returns (G, M, N) bf16."""
+    _require_cuda(a, "gemm_bf16_tn")
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.dim() != 3 or b.dim() != 3:
+        raise TypeError("gemm_bf16_tn: (G, M, K) x (G, N, K) bf16 operands expected")
+    G, M, K = a.shape
+    N = b.shape[1]
+    if b.shape[0] != G or b.shape[2] != K or a.stride(2) != 1 or b.stride(2) != 1:
+        raise RuntimeError("gemm_bf16_tn: shape / stride mismatch")
+    c = torch.empty((G, M, N), dtype=torch.bfloat16, device=a.device)
+    rs = None
+    if row_scale is not None:
+        rs = _f32c(row_scale, "row_scale")
+        assert tuple(rs.shape) == (G, M)
+    st = _cabi.lib().dm_gemm_bf16_tn(a.data_ptr(), a.stride(0), a.stride(1), b.data_ptr(), b.stride(0), b.stride(1),
+                                     c.data_ptr(), c.stride(0), c.stride(1), None if rs is None else rs.data_ptr(),
+                                     G, M, N, K, _stream_handle(a.device))
+    _cabi.check(st, "dm_gemm_bf16_tn")
+    LAUNCH_COUNTER["kernels"] += 1
+    return c

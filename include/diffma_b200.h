@@ -188,6 +188,17 @@ int dm_spiral_post_mix(const float* x, const float* skip, const void* ab, const 
                        const float* b3, const float* mod, int64_t mod_batch_stride, float* out, int32_t batch,
                        int32_t seqlen, int32_t d_model, int32_t act_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Batched bf16 GEMM on tcgen05 / TMEM / TMA:  C[g] = rowscale[g] (.) (A[g] . B[g]^T), fp32 accumulation.
+ *   A (groups, M, K), B (groups, N, K), C (groups, M, N), all bf16, K (resp. N) contiguous, strides in elements and
+ *   multiples of 8; row_scale (groups, M) fp32 or NULL.  Replaces the cuBLAS calls behind the reference's
+ *   in-projection (block/mamba.py:333-337, block/mamba2.py:382) and out-projection (inside mamba_inner_fn /
+ *   mamba_split_conv1d_scan_combined); the row scale carries the soft mask  (x*w).W = w (.) (x.W).
+ * ---------------------------------------------------------------------------------------------------- */
+int dm_gemm_bf16_tn(const void* A, int64_t a_group_stride, int64_t a_row_stride, const void* B, int64_t b_group_stride,
+                    int64_t b_row_stride, void* C, int64_t c_group_stride, int64_t c_row_stride, const float* row_scale,
+                    int32_t groups, int32_t M, int32_t N, int32_t K, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------ */
 int dm_version(void);                     /* DM_ABI_VERSION of the loaded library                        */
 const char* dm_status_string(int status);

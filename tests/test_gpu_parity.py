@@ -208,3 +208,37 @@ def test_fused_block_path_equals_module_path(dev, use_m2, dtype):
             plain = net(b["x"], b["t"], b["y"], b["y2"], b["w"]).float().detach()
     tol = dict(rtol=2e-4, atol=2e-4) if dtype == "fp32" else dict(rtol=3e-2, atol=3e-2)
     torch.testing.assert_close(fused, plain, **tol)
+
+
+@pytest.mark.parametrize("G,M,N,K", [(1, 128, 128, 64), (2, 256, 256, 512), (2, 3136, 2048, 512), (2, 3136, 512, 3072),
+                                     (1, 200, 136, 72), (3, 77, 264, 1024)])
+def test_tcgen05_gemm_matches_fp32_reference(dev, G, M, N, K):
+    """dm_gemm_bf16_tn (TMA -> tcgen05.mma -> TMEM -> tcgen05.ld epilogue) vs an fp32 matmul of the same bf16 operands,
+    incl. ragged M / N / K tails and the row-scale epilogue.  Tolerance: one bf16 rounding of the output (2^-8)."""
+    from diffma_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(G, M, K, generator=g).bfloat16().to(dev)
+    b = torch.randn(G, N, K, generator=g).bfloat16().to(dev)
+    rs = (torch.rand(G, M, generator=g) + 0.5).to(dev)
+    ref = torch.bmm(a.float(), b.float().transpose(1, 2))
+    c = ops.gemm_bf16_tn(a, b).float()
+    c2 = ops.gemm_bf16_tn(a, b, rs).float()
+    scale = ref.abs().max().item()
+    assert (c - ref).abs().max().item() <= 4e-3 * scale
+    assert (c2 - ref * rs[..., None]).abs().max().item() <= 6e-3 * scale
+
+
+def test_tcgen05_gemm_path_in_block(dev, monkeypatch):
+    """The fused block with DIFFMA_GEMM=tcgen05 (projections on dm_gemm_bf16_tn) equals the library-GEMM path."""
+    from diffma_b200 import blocks, model as M, synth
+    torch.manual_seed(0)
+    net = M.DiffMa_models["DiffMa-S/2"](input_size=28, dt_rank=16, d_state=16, use_mamba2=False).eval()
+    synth.fill_trained_like_(net, seed=11)
+    net = net.to(dev)
+    b = synth.synthetic_batch(2, tokens=196, seed=21, device=dev)
+    outs = {}
+    for flag in (False, True):
+        monkeypatch.setattr(blocks, "_USE_TCGEN05_GEMM", flag)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs[flag] = net(b["x"], b["t"], b["y"], b["y2"], b["w"]).float()
+    torch.testing.assert_close(outs[True], outs[False], rtol=3e-2, atol=3e-2)

@@ -46,8 +46,9 @@ def _worker(rank, world, port, q):
     y = torch.randn(4, 16, generator=g)
     t = torch.tensor([3, 250, 600, 999])
     sl = slice(rank * 2, rank * 2 + 2)
-    loss = d.training_losses(ddp, x[sl], t[sl], dict(y=y[sl], y2=None, w=None), noise=noise[sl])["loss"].mean()
-    loss.backward()
+    with torch.enable_grad():
+        loss = d.training_losses(ddp, x[sl], t[sl], dict(y=y[sl], y2=None, w=None), noise=noise[sl])["loss"].mean()
+        loss.backward()
     grads = [p.grad.clone() for p in net.parameters()]
     mx = bench.max_over_ranks(float(rank + 1), world, torch.device("cpu"))
     bench.barrier(world)
@@ -78,7 +79,8 @@ def test_ddp_gloo_gradients_equal_single_process():
     noise = torch.randn(4, 4, 8, 8, generator=g)
     y = torch.randn(4, 16, generator=g)
     t = torch.tensor([3, 250, 600, 999])
-    d.training_losses(net, x, t, dict(y=y, y2=None, w=None), noise=noise)["loss"].mean().backward()
+    with torch.enable_grad():     # other test modules switch grad mode off globally
+        d.training_losses(net, x, t, dict(y=y, y2=None, w=None), noise=noise)["loss"].mean().backward()
     for a, p in zip(grads, net.parameters()):
         torch.testing.assert_close(torch.from_numpy(a), p.grad, rtol=1e-5, atol=1e-6)
 
