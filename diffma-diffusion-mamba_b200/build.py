@@ -57,7 +57,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [cc, *ARCH, *FLAGS, "-c", src, "-o", obj]
+        extra = os.environ.get("DM_NVCC_EXTRA", "").split()
+        cmd = [cc, *ARCH, *FLAGS, *extra, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
 

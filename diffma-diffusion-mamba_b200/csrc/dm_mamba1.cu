@@ -512,6 +512,45 @@ __device__ __forceinline__ float softplus_fast(float x) {
     const float r = e < 0.0078125f ? small : big;
     return x > 20.0f ? x : r;
 }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// 2^x for a packed pair of non-positive arguments on the FMA / ALU pipes instead of the MUFU: round-to-nearest split
+// x = n + f (magic-number add), degree-5 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 2.3e-7 in
+// fp32, the same 2 ulp class as ex2.approx), exponent inserted with an integer add.  The scan is bound by the MUFU
+// pipe (16 lanes/clk/SM) while the FMA pipe idles at ~20 %, so a fixed share of the 16 decays per token goes here.
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
+    float x0, x1;
+    unpack2(x2, x0, x1);
+    x2 = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+    const uint64_t magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
+    const uint64_t t = add2(x2, magic);                       // low mantissa bits of t = round(x)
+    const uint64_t n = add2(t, nmagic);
+    const uint64_t f = fma2(n, pack2(-1.0f, -1.0f), x2);      // f = x - n in [-0.5, 0.5]
+    uint64_t p = pack2(0.0013266970636323094f, 0.0013266970636323094f);
+    p = fma2(p, f, pack2(0.009675459936261177f, 0.009675459936261177f));
+    p = fma2(p, f, pack2(0.05550742521882057f, 0.05550742521882057f));
+    p = fma2(p, f, pack2(0.24022121727466583f, 0.24022121727466583f));
+    p = fma2(p, f, pack2(0.6931469440460205f, 0.6931469440460205f));
+    p = fma2(p, f, pack2(1.0000001192092896f, 1.0000001192092896f));
+    float p0, p1, t0, t1;
+    unpack2(p, p0, p1);
+    unpack2(t, t0, t1);
+    return pack2(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)),
+                 __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+}
+#ifndef DM_POLY_PAIRS
+#define DM_POLY_PAIRS 0       // of the 8 state pairs per (token, channel): how many decays are evaluated by exp2_poly2
+#endif
+
+// non-volatile MMA: lets ptxas interleave independent accumulator chains
+__device__ __forceinline__ void mma_nv(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void ldmatrix_x4_u(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -628,16 +667,26 @@ __global__ void __launch_bounds__(32, 12) m1_scan_kernel(const __grid_constant__
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 {
-                    float a0, a1;
-                    unpack2(mul2(dt2, A2[ch][2 * q]), a0, a1);
-                    const uint64_t dA = pack2(ex2_approx(a0), ex2_approx(a1));
+                    uint64_t dA;
+                    if (2 * q < DM_POLY_PAIRS) {
+                        dA = exp2_poly2(mul2(dt2, A2[ch][2 * q]));
+                    } else {
+                        float a0, a1;
+                        unpack2(mul2(dt2, A2[ch][2 * q]), a0, a1);
+                        dA = pack2(ex2_approx(a0), ex2_approx(a1));
+                    }
                     h[ch][2 * q] = fma2(dA, h[ch][2 * q], mul2(dtu2, Bq[q].x));
                     y0 = fma2(h[ch][2 * q], Cq[q].x, y0);
                 }
                 {
-                    float a0, a1;
-                    unpack2(mul2(dt2, A2[ch][2 * q + 1]), a0, a1);
-                    const uint64_t dA = pack2(ex2_approx(a0), ex2_approx(a1));
+                    uint64_t dA;
+                    if (2 * q + 1 < DM_POLY_PAIRS) {
+                        dA = exp2_poly2(mul2(dt2, A2[ch][2 * q + 1]));
+                    } else {
+                        float a0, a1;
+                        unpack2(mul2(dt2, A2[ch][2 * q + 1]), a0, a1);
+                        dA = pack2(ex2_approx(a0), ex2_approx(a1));
+                    }
                     h[ch][2 * q + 1] = fma2(dA, h[ch][2 * q + 1], mul2(dtu2, Bq[q].y));
                     y1 = fma2(h[ch][2 * q + 1], Cq[q].y, y1);
                 }
@@ -646,7 +695,7 @@ __global__ void __launch_bounds__(32, 12) m1_scan_kernel(const __grid_constant__
             unpack2(y0, ya, yb);
             unpack2(y1, yc, yd);
             const float y = fmaf(Dc[ch], uu, (ya + yb) + (yc + yd));
-            const float o = y * silu_fast(zz);
+            const float o = y * (kSplit ? silu_fast(zz) : silu_tanh(zz));    // bf16 output: 1 MUFU (tanh) is enough
             *reinterpret_cast<T*>(out_lane + row_off + ch * 32 * static_cast<int>(sizeof(T))) = from_f32<T>(o);
         }
     };
@@ -676,21 +725,36 @@ __global__ void __launch_bounds__(32, 12) m1_scan_kernel(const __grid_constant__
                 a_lo[ks][0] = row[16 + ks * 8 + q]; a_lo[ks][1] = 0u; a_lo[ks][2] = row[16 + ks * 8 + 4 + q]; a_lo[ks][3] = 0u;
             }
 #pragma unroll
-            for (int nt = 0; nt < kSC / 8; ++nt) {
-                float dacc[4] = {0.f, 0.f, 0.f, 0.f};
-                uint32_t bw[4];
-                ldmatrix_x4_u(bw, smem_u32(&S.wdt[0][nt * 8 + (lane & 7)][(lane >> 3) * 8]));
+            // 4 n-tiles at a time, MMA chains interleaved (4 independent accumulators in flight)
+#pragma unroll
+            for (int half = 0; half < kSC / 32; ++half) {
+                float dacc[4][4];
+                uint32_t bw[4][4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dacc[t][i] = 0.f;
+                    ldmatrix_x4_u(bw[t], smem_u32(&S.wdt[0][(half * 4 + t) * 8 + (lane & 7)][(lane >> 3) * 8]));
+                }
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
-                    mma_bf16_16816(dacc, a_hi[ks], bw[2 * ks], bw[2 * ks + 1]);
-                    mma_bf16_16816(dacc, a_lo[ks], bw[2 * ks], bw[2 * ks + 1]);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) mma_nv(dacc[t], a_hi[ks], bw[t][2 * ks], bw[t][2 * ks + 1]);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) mma_nv(dacc[t], a_lo[ks], bw[t][2 * ks], bw[t][2 * ks + 1]);
                 }
                 if constexpr (kSplit) {
-                    ldmatrix_x4_u(bw, smem_u32(&S.wdt[kSplit ? 1 : 0][nt * 8 + (lane & 7)][(lane >> 3) * 8]));
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) mma_bf16_16816(dacc, a_hi[ks], bw[2 * ks], bw[2 * ks + 1]);
+                    for (int t = 0; t < 4; ++t)
+                        ldmatrix_x4_u(bw[t], smem_u32(&S.wdt[kSplit ? 1 : 0][(half * 4 + t) * 8 + (lane & 7)][(lane >> 3) * 8]));
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) mma_nv(dacc[t], a_hi[ks], bw[t][2 * ks], bw[t][2 * ks + 1]);
                 }
-                *reinterpret_cast<float2*>(&S.ds[r][nt * 8 + 2 * q]) = make_float2(dacc[0], dacc[1]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    *reinterpret_cast<float2*>(&S.ds[r][(half * 4 + t) * 8 + 2 * q]) = make_float2(dacc[t][0], dacc[t][1]);
             }
         }
         __syncwarp();

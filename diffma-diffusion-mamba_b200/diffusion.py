@@ -79,6 +79,7 @@ class SpacedDiffusion:
         self.use_timesteps = set(use_timesteps)
         self.learn_sigma = learn_sigma
         self.sigma_small = sigma_small
+        self.want_pred_xstart = True        # the graphed sampler switches the unused pred_xstart output off
         # respace.py:71-82: re-derive betas so that alphas_cumprod matches at the kept steps
         base_acp = np.cumprod(1.0 - base_betas)
         betas, self.timestep_map, last = [], [], 1.0
@@ -180,6 +181,17 @@ class SpacedDiffusion:
     def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None,
                  model_kwargs=None, noise=None):
         assert cond_fn is None, "classifier guidance is never used by DiffMa's scripts"
+        if (x.is_cuda and self.learn_sigma and denoised_fn is None and not torch.is_grad_enabled()
+                and x.dtype == torch.float32 and t.dtype == torch.int64):
+            # device path: the whole posterior update (table gather included) is one kernel (dm_p_sample_update)
+            from . import ops
+            model_output = self._call_model(model, x, t, model_kwargs).float().contiguous()
+            if noise is None:
+                noise = torch.randn_like(x)
+            tab, _ = self._tables(x.device)
+            sample, pred = ops.p_sample_update(model_output, x.contiguous(), noise.contiguous(), tab, t, clip_denoised,
+                                               want_pred_xstart=self.want_pred_xstart)
+            return {"sample": sample, "pred_xstart": pred}
         out = self.p_mean_variance(model, x, t, clip_denoised, denoised_fn, model_kwargs)
         if noise is None:
             noise = torch.randn_like(x)
@@ -270,15 +282,22 @@ class GraphedSampler:
     """
 
     def __init__(self, diffusion: SpacedDiffusion, model: Callable, shape, model_kwargs: dict, device,
-                 clip_denoised: bool = False, warmup: int = 2, use_graph: bool = True):
+                 clip_denoised: bool = False, warmup: int = 2, use_graph: bool = True, pool_y2: bool = False):
         from . import ops
         self.diffusion, self.model = diffusion, model
         self.x = torch.zeros(*shape, device=device)
         self.t = torch.zeros(shape[0], dtype=torch.long, device=device)
         self.kw = {k: v.clone() for k, v in model_kwargs.items()}
+        # y2 only enters the model through its token mean (reference model.py:276), which is constant over the 250
+        # steps: pool it once per batch outside the graph (needs a model that accepts a pooled (N, D) y2: ours does)
+        self.model_kw = dict(self.kw)
+        self.y2_pooled = None
+        if pool_y2 and "y2" in self.kw and self.kw["y2"].dim() == 3:
+            self.y2_pooled = self.kw["y2"].mean(dim=1)
+            self.model_kw["y2"] = self.y2_pooled
         self.clip = clip_denoised
-        self.noise = torch.zeros(*shape, device=device)
         diffusion._tables(device)
+        diffusion.want_pred_xstart = False
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side), torch.no_grad():
@@ -296,7 +315,7 @@ class GraphedSampler:
                 self._step()
 
     def _step(self):
-        out = self.diffusion.p_sample(self.model, self.x, self.t, clip_denoised=self.clip, model_kwargs=self.kw)
+        out = self.diffusion.p_sample(self.model, self.x, self.t, clip_denoised=self.clip, model_kwargs=self.model_kw)
         self.x.copy_(out["sample"])
         self.t.sub_(1).clamp_(min=0)
 
@@ -312,6 +331,7 @@ class GraphedSampler:
         if model_kwargs is not None:
             for k, v in model_kwargs.items():
                 self.kw[k].copy_(v)
+            self._pool()
         self.t.fill_(self.diffusion.num_timesteps - 1)
 
     def load(self, x_host: torch.Tensor, t_host: torch.Tensor, kw_host: dict):
@@ -320,6 +340,11 @@ class GraphedSampler:
         self.t.copy_(t_host, non_blocking=True)
         for k, v in kw_host.items():
             self.kw[k].copy_(v, non_blocking=True)
+        self._pool()
+
+    def _pool(self):
+        if self.y2_pooled is not None:
+            torch.mean(self.kw["y2"], dim=1, out=self.y2_pooled)
 
     @torch.no_grad()
     def run(self, noise: torch.Tensor, model_kwargs: Optional[dict] = None) -> torch.Tensor:

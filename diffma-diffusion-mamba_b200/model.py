@@ -157,38 +157,86 @@ class DiffMa(nn.Module):
         x = x.reshape(x.shape[0], h, w, p, p, c)
         return torch.einsum("nhwpqc->nchpwq", x).reshape(x.shape[0], c, h * p, h * p)
 
+    # ---- inference-only caches (keyed on parameter versions, rebuilt when weights change) ----------------
+    def _cached(self, name, params, build):
+        key = (params[0].device, tuple(p._version for p in params))
+        slot = self.__dict__.setdefault("_icache", {})
+        if name not in slot or slot[name][0] != key:
+            with torch.no_grad():
+                slot[name] = (key, build())
+        return slot[name][1]
+
     def _fused_mods(self, c, act):
-        """adaLN of EVERY block in one GEMM: c is the same for all blocks of a forward (reference recomputes it per
-        block, block/mamba_block.py:101).  Returns (B, depth, 3D) fp32; weights cached in the act dtype."""
+        """adaLN of EVERY block and of the final layer in one GEMM: c is the same for all of them in a forward (the
+        reference recomputes it per block, block/mamba_block.py:101).  Returns blocks (B, depth, 3D) and final (B, 2D),
+        fp32; weights cached in the act dtype."""
         import torch.nn.functional as F
-        ps = [p for blk in self.blocks for p in (blk.adaLN_modulation[1].weight, blk.adaLN_modulation[1].bias)]
-        key = (act, ps[0].device, tuple(p._version for p in ps))
-        cache = getattr(self, "_ada_cache", None)
-        if cache is None or cache["key"] != key:
-            cache = {"key": key,
-                     "w": torch.cat([blk.adaLN_modulation[1].weight for blk in self.blocks]).to(act).contiguous(),
-                     "b": torch.cat([blk.adaLN_modulation[1].bias for blk in self.blocks]).to(act).contiguous()}
-            self._ada_cache = cache
+        lins = [blk.adaLN_modulation[1] for blk in self.blocks] + [self.final_layer.adaLN_modulation[1]]
+        ps = [p for lin in lins for p in (lin.weight, lin.bias)]
+        w, b = self._cached(f"ada_{act}", ps, lambda: (torch.cat([lin.weight for lin in lins]).to(act).contiguous(),
+                                                        torch.cat([lin.bias for lin in lins]).to(act).contiguous()))
         with torch.autocast("cuda", enabled=False):
-            mods = F.linear(F.silu(c.float()).to(act), cache["w"], cache["b"]).float()
-        return mods.view(c.shape[0], self.depth, -1)
+            mods = F.linear(F.silu(c.float()).to(act), w, b).float()
+        D = self.pos_embed.shape[-1]
+        nb = self.depth * 3 * D
+        return mods[:, :nb].view(c.shape[0], self.depth, 3 * D), mods[:, nb:]
+
+    def _t_embedding(self, t):
+        """t_embedder(t) for integer timesteps from a (1000, D) table built once per weights version: the embedder is a
+        pure function of the integer step (reference model.py:49-85 recomputes cos/sin + 2 Linears every call)."""
+        if t.dtype not in (torch.int64, torch.int32):
+            return self.t_embedder(t)
+        ps = list(self.t_embedder.parameters())
+        table = self._cached("temb", ps, lambda: self.t_embedder(torch.arange(1000, device=ps[0].device)).float())
+        return table.index_select(0, t.long())
+
+    def _embed_patches(self, x):
+        """PatchEmbed conv (kernel = stride = patch) as one matmul on unfolded patches + (bias + pos_embed) table."""
+        p = self.patch_size
+        N, C, H, W = x.shape
+        g = H // p
+        wb = self._cached("patch", [self.x_embedder.proj.weight, self.x_embedder.proj.bias, self.pos_embed],
+                          lambda: (self.x_embedder.proj.weight.reshape(self.x_embedder.proj.weight.shape[0], -1).t().contiguous().float(),
+                                   (self.pos_embed[0] + self.x_embedder.proj.bias[None, :]).float().contiguous()))
+        patches = x.float().view(N, C, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(N, g * g, C * p * p)
+        with torch.autocast("cuda", enabled=False):
+            return torch.baddbmm(wb[1].unsqueeze(0), patches, wb[0].unsqueeze(0).expand(N, -1, -1))
 
     def forward(self, x, t, y, y2, w):
-        """x (N,C,H,W), t (N,), y (N,D), y2 (N,T,D), w (N,T,1) -> (N, out_channels, H, W)  [model.py:264-301]"""
-        x = self.x_embedder(x) + self.pos_embed
-        t = self.t_embedder(t)
-        c = torch.cat((t + y, t + torch.mean(y2, dim=1)), dim=1)
-        fused = (not torch.is_grad_enabled()) and x.is_cuda and self.block_type == "spiral" and x.shape[-1] == 512
-        outs = []
+        """x (N,C,H,W), t (N,), y (N,D), y2 (N,T,D) [or already pooled (N,D)], w (N,T,1) -> (N, out_channels, H, W)
+        [reference model.py:264-301]"""
+        fused = ((not torch.is_grad_enabled()) and x.is_cuda and self.block_type == "spiral"
+                 and self.pos_embed.shape[-1] == 512 and self.x_embedder.proj.stride[0] == self.patch_size)
         if fused:
+            from . import ops
             from .mixer import _act_dtype
-            x = x.float().contiguous()
-            mods = self._fused_mods(c, _act_dtype(x))
+            h = self._embed_patches(x)
+            te = self._t_embedding(t)
+            y2m = y2 if y2.dim() == 2 else torch.mean(y2, dim=1)
+            c = torch.cat((te + y, te + y2m), dim=1)
+            act = _act_dtype(h)
+            mods, fmod = self._fused_mods(c, act)
+            outs = []
             for i in range(self.depth):
                 skip = outs[self.depth - i - 1] if (i > self.depth / 2) else None
-                x = self.blocks[i]._forward_fused(x, c, w, skip, mods[:, i])
-                outs.append(x)
-            return self.unpatchify(self.final_layer(x, c))
+                h = self.blocks[i]._forward_fused(h, c, w, skip, mods[:, i])
+                outs.append(h)
+            # final layer: LN (no affine, eps 1e-6) + modulate through the same row kernel, then the small Linear
+            D = h.shape[-1]
+            ones, zeros = self._cached("fl_affine", [self.pos_embed], lambda: (torch.ones(D, device=h.device),
+                                                                               torch.zeros(D, device=h.device)))
+            hn = ops.spiral_pre(h, None, ones, zeros, fmod, None, act, eps=1e-6)[0].view(h.shape)
+            with torch.autocast("cuda", enabled=False):
+                lw, lb = self._cached(f"fl_lin_{act}", [self.final_layer.linear.weight, self.final_layer.linear.bias],
+                                      lambda: (self.final_layer.linear.weight.to(act).contiguous(),
+                                               self.final_layer.linear.bias.to(act).contiguous()))
+                o = torch.nn.functional.linear(hn, lw, lb)
+            return self.unpatchify(o)
+        x = self.x_embedder(x) + self.pos_embed
+        t = self.t_embedder(t)
+        y2m = y2 if y2.dim() == 2 else torch.mean(y2, dim=1)
+        c = torch.cat((t + y, t + y2m), dim=1)
+        outs = []
         for i in range(self.depth):
             if i == 0:
                 x = self.blocks[i](x, c, w)

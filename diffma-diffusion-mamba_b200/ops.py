@@ -440,14 +440,14 @@ def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
     return t
 
 
-def spiral_pre(x, skip, ln_weight, ln_bias, mod, w, act_dtype) -> torch.Tensor:
+def spiral_pre(x, skip, ln_weight, ln_bias, mod, w, act_dtype, eps: float = 1e-5) -> torch.Tensor:
     """x (B,L,D) fp32 [+ skip] -> (2, B*L, D) act dtype: [modulate(LN(x)) ; modulate(LN(x)) * w]."""
     B, L, D = x.shape
     out2 = torch.empty((2, B * L, D), dtype=act_dtype, device=x.device)
     st = _cabi.lib().dm_spiral_pre(_f32c(x, "x").data_ptr(), None if skip is None else _f32c(skip, "skip").data_ptr(),
                                    _f32c(ln_weight, "ln_weight").data_ptr(), _f32c(ln_bias, "ln_bias").data_ptr(),
                                    _mod2d(mod).data_ptr(), mod.stride(0),
-                                   None if w is None else _f32c(w, "w").data_ptr(), out2.data_ptr(), B, L, D, 1e-5,
+                                   None if w is None else _f32c(w, "w").data_ptr(), out2.data_ptr(), B, L, D, eps,
                                    _dtype_code(out2), _stream_handle(x.device))
     _cabi.check(st, "dm_spiral_pre")
     LAUNCH_COUNTER["kernels"] += 1
@@ -512,3 +512,22 @@ def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, row_scale: Optional[torch.Ten
     _cabi.check(st, "dm_gemm_bf16_tn")
     LAUNCH_COUNTER["kernels"] += 1
     return c
+
+
+def p_sample_update(model_out, x, noise, table, t, clip_denoised=False, want_pred_xstart=True):
+    """One reverse-diffusion update on ``dm_p_sample_update``.  model_out (N, 2C, H, W), x / noise (N, C, H, W) fp32
+    contiguous, table (9, n_steps) fp32 (diffusion._ROWS order), t (N,) int64 -> (sample, pred_xstart | None)."""
+    _require_cuda(x, "p_sample_update")
+    N = x.shape[0]
+    chw = x.numel() // N
+    if tuple(model_out.shape) != (N, 2 * x.shape[1]) + tuple(x.shape[2:]) or t.dtype != torch.int64:
+        raise RuntimeError("p_sample_update: model_out must be (N, 2C, H, W) and t int64")
+    sample = torch.empty_like(x)
+    pred = torch.empty_like(x) if want_pred_xstart else None
+    st = _cabi.lib().dm_p_sample_update(_f32c(model_out, "model_out").data_ptr(), _f32c(x, "x").data_ptr(),
+                                        _f32c(noise, "noise").data_ptr(), _f32c(table, "table").data_ptr(),
+                                        t.contiguous().data_ptr(), sample.data_ptr(), _ptr(pred), N, chw, table.shape[1],
+                                        int(bool(clip_denoised)), _stream_handle(x.device))
+    _cabi.check(st, "dm_p_sample_update")
+    LAUNCH_COUNTER["kernels"] += 1
+    return sample, pred

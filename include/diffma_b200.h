@@ -189,6 +189,18 @@ int dm_spiral_post_mix(const float* x, const float* skip, const void* ab, const 
                        int32_t seqlen, int32_t d_model, int32_t act_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * One reverse-diffusion update as one elementwise kernel (reference diffusion/gaussian_diffusion.py p_mean_variance
+ * :254-332 with LEARNED_RANGE variance + epsilon prediction, and p_sample :376-417):
+ *   model_out (N, 2C, H, W) fp32 = [eps | v], x (N, C, H, W), noise like x, t (N) int64 step indices,
+ *   table (9, n_steps) fp32 rows: sqrt_acp, sqrt_1m_acp, sqrt_recip_acp, sqrt_recipm1_acp, posterior_variance,
+ *   posterior_log_variance_clipped, posterior_mean_coef1, posterior_mean_coef2, log_betas.
+ *   sample = mean + [t != 0] * exp(0.5*logvar) * noise ; pred_xstart optional (may be NULL).  chw = C*H*W.
+ * ---------------------------------------------------------------------------------------------------- */
+int dm_p_sample_update(const float* model_out, const float* x, const float* noise, const float* table, const int64_t* t,
+                       float* sample, float* pred_xstart, int32_t batch, int32_t chw, int32_t n_steps,
+                       int32_t clip_denoised, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Batched bf16 GEMM on tcgen05 / TMEM / TMA:  C[g] = rowscale[g] (.) (A[g] . B[g]^T), fp32 accumulation.
  *   A (groups, M, K), B (groups, N, K), C (groups, M, N), all bf16, K (resp. N) contiguous, strides in elements and
  *   multiples of 8; row_scale (groups, M) fp32 or NULL.  Replaces the cuBLAS calls behind the reference's

@@ -242,3 +242,23 @@ def test_tcgen05_gemm_path_in_block(dev, monkeypatch):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             outs[flag] = net(b["x"], b["t"], b["y"], b["y2"], b["w"]).float()
     torch.testing.assert_close(outs[True], outs[False], rtol=3e-2, atol=3e-2)
+
+
+def test_p_sample_update_kernel_matches_reference_golden(dev):
+    """dm_p_sample_update (one kernel) vs values recorded from the REFERENCE's own diffusion/ package
+    (tests/golden/diffusion.npz: p_mean_variance + the explicit-noise p_sample formula)."""
+    from diffma_b200.diffusion import create_diffusion
+    g = load("diffusion.npz")
+    for tag, resp in (("s250", "250"), ("full", "")):
+        d = create_diffusion(resp)
+        gen = torch.Generator().manual_seed(7)
+        x = torch.randn(4, 4, 28, 28, generator=gen)
+        n = torch.randn(4, 4, 28, 28, generator=gen)
+        t = torch.tensor([0, 1, d.num_timesteps // 2, d.num_timesteps - 1])
+
+        def fake_model(xx, tt, **kw):
+            return torch.cat([0.3 * xx + 0.001 * tt.view(-1, 1, 1, 1).float(), torch.tanh(xx)], dim=1)
+
+        out = d.p_sample(fake_model, x.to(dev), t.to(dev), clip_denoised=False, noise=n.to(dev))
+        np.testing.assert_allclose(out["sample"].cpu().numpy(), g[f"{tag}_p_sample"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(out["pred_xstart"].cpu().numpy(), g[f"{tag}_pmv_pred_xstart"], rtol=2e-5, atol=2e-5)
