@@ -469,8 +469,9 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
 // as packed fp32 pairs.  Two channels per lane halve the shared-memory (MIO) traffic for B/C per MUFU op and
 // give 32 independent ex2 per token, so ~10 resident warps per SM already saturate the MUFU pipe; at the
 // BASELINE shape (1536 warp-units) every unit is resident in a single wave on 148 SMs.
-constexpr int kSC = 64;       // channels per scan warp
-template <typename T> struct ScanSmem {
+// CPL = channels per lane (2 for the big shapes, 1 when there are too few warp-units to fill the SMs otherwise)
+template <typename T, int CPL> struct ScanSmem {
+    static constexpr int kSC = 32 * CPL;     // channels per scan warp
     float xd[2][kCH][kE];                    // x_dbl chunk, rows as above
     T us[2][kCH][kSC];
     T zs[2][kCH][kSC];
@@ -557,14 +558,15 @@ __device__ __forceinline__ void ldmatrix_x4_u(uint32_t (&r)[4], uint32_t addr) {
                  : "r"(addr));
 }
 
-template <typename T>
-__global__ void __launch_bounds__(32, 12) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
+template <typename T, int CPL>
+__global__ void __launch_bounds__(32, CPL == 2 ? 12 : 20) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
     constexpr bool kSplit = sizeof(T) == 4;
+    constexpr int kSC = 32 * CPL;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x;
     const int unit = blockIdx.x;
     if (unit >= n_units) return;
-    ScanSmem<T>& S = *reinterpret_cast<ScanSmem<T>*>(smem_raw);
+    ScanSmem<T, CPL>& S = *reinterpret_cast<ScanSmem<T, CPL>*>(smem_raw);
 
     const int D = p.D, L = p.L;
     const int slices = D / kSC;
@@ -600,10 +602,10 @@ __global__ void __launch_bounds__(32, 12) m1_scan_kernel(const __grid_constant__
     }
 
     // per-channel constants: A*log2(e) as 8 packed pairs per channel
-    uint64_t A2[2][kN / 2];
-    float dtb[2], Dc[2];
+    uint64_t A2[CPL][kN / 2];
+    float dtb[CPL], Dc[CPL];
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
+    for (int ch = 0; ch < CPL; ++ch) {
         const int c = c0 + ch * 32 + lane;
 #pragma unroll
         for (int n = 0; n < kN; n += 4) {
@@ -643,22 +645,21 @@ __global__ void __launch_bounds__(32, 12) m1_scan_kernel(const __grid_constant__
         cp_async_commit();
     };
 
-    uint64_t h[2][kN / 2];
+    uint64_t h[CPL][kN / 2];
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch)
+    for (int ch = 0; ch < CPL; ++ch)
 #pragma unroll
         for (int n = 0; n < kN / 2; ++n) h[ch][n] = 0ull;      // bit pattern of (0.f, 0.f)
 
     // one token of the recurrence for both channels of the lane
-    auto token = [&](int buf, int jj, float dt0, float dt1) {
-        const float dtv[2] = {dt0, dt1};
+    auto token = [&](int buf, int jj, const float (&dtv)[CPL]) {
         const ulonglong2* bc = reinterpret_cast<const ulonglong2*>(&S.xd[buf][jj][kR]);
         ulonglong2 Bq[4], Cq[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) { Bq[q] = bc[q]; Cq[q] = bc[4 + q]; }
         const int row_off = S.rows[buf][jj];
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
+        for (int ch = 0; ch < CPL; ++ch) {
             const float uu = to_f32<T>(S.us[buf][jj][ch * 32 + lane]);
             const float zz = to_f32<T>(S.zs[buf][jj][ch * 32 + lane]);
             const float dt = dtv[ch], dtu = dt * uu;
@@ -762,19 +763,22 @@ __global__ void __launch_bounds__(32, 12) m1_scan_kernel(const __grid_constant__
         if (j0 + kCH <= L) {
             // full chunk: softplus for all 8 tokens first (16 independent MUFU chains, off the recurrence's
             // critical path), then straight-line recurrence without predicates
-            float dtv[kCH][2];
+            float dtv[kCH][CPL];
 #pragma unroll
-            for (int jj = 0; jj < kCH; ++jj) {
-                dtv[jj][0] = softplus_fast(S.ds[jj][lane] + dtb[0]);
-                dtv[jj][1] = softplus_fast(S.ds[jj][32 + lane] + dtb[1]);
-            }
+            for (int jj = 0; jj < kCH; ++jj)
 #pragma unroll
-            for (int jj = 0; jj < kCH; ++jj) token(buf, jj, dtv[jj][0], dtv[jj][1]);
+                for (int ch = 0; ch < CPL; ++ch) dtv[jj][ch] = softplus_fast(S.ds[jj][ch * 32 + lane] + dtb[ch]);
+#pragma unroll
+            for (int jj = 0; jj < kCH; ++jj) token(buf, jj, dtv[jj]);
         } else {
             const int nrows = L - j0;
 #pragma unroll 1
-            for (int jj = 0; jj < nrows; ++jj)
-                token(buf, jj, softplus_fast(S.ds[jj][lane] + dtb[0]), softplus_fast(S.ds[jj][32 + lane] + dtb[1]));
+            for (int jj = 0; jj < nrows; ++jj) {
+                float dtv[CPL];
+#pragma unroll
+                for (int ch = 0; ch < CPL; ++ch) dtv[ch] = softplus_fast(S.ds[jj][ch * 32 + lane] + dtb[ch]);
+                token(buf, jj, dtv);
+            }
         }
         __syncwarp();
     }
@@ -816,16 +820,27 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream) {
     }
     // kernel S
     if (phases & 2) {
-        const int n_units = n_seq * (p.D / kSC);
-        const size_t bytes = sizeof(ScanSmem<T>);
-        static thread_local bool configured = false;
-        if (!configured) {
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(bytes)));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            configured = true;
+        static thread_local int n_sm = 0;
+        if (n_sm == 0) {
+            int dev = 0;
+            DM_CUDA_TRY(cudaGetDevice(&dev));
+            DM_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(ScanSmem<T, 2>))));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(ScanSmem<T, 1>))));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
-        m1_scan_kernel<T><<<n_units, 32, bytes, stream>>>(p, n_units);
+        // two channels per lane (fewer shared-memory reads per MUFU op, 168 registers) when that still leaves >= 8
+        // warps per SM; otherwise one channel per lane doubles the number of warp-units (small batches, config C5)
+        const int units2 = n_seq * (p.D / 64);
+        if (units2 >= 8 * n_sm) {
+            m1_scan_kernel<T, 2><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
+        } else {
+            const int units1 = n_seq * (p.D / 32);
+            m1_scan_kernel<T, 1><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
+        }
         DM_CUDA_TRY(cudaGetLastError());
     }
     return DM_OK;
