@@ -86,27 +86,41 @@ class Mamba1ScanFn(torch.autograd.Function):
         _cabi.check(lib.dm_mamba1_scan_bwd(C.byref(a), gr, 1, st), "dm_mamba1_scan_bwd(phase 1)")
         T = B * K * L
         dWx, dWdt = [], []
-        for g in range(G):
-            w = weights[g]
-            dd = ddelta[g].view(T, D)
-            dxd = d_x_dbl[g].view(T, E)
-            dxd[:, :R] = dd @ w.dt_proj_weight.float()                                   # d dt_low
-            halves = x_dbl[g].view(T, E)[:, :R].contiguous().view(torch.bfloat16)        # (T, 2R): [hi | lo]
-            dt_low = halves[:, :R].float() + halves[:, R:].float()
-            dWdt.append(dd.t() @ dt_low)
-            du[g].view(T, D).addmm_(dxd, w.x_proj_weight.float())                        # du += d_x_dbl . W_x
-            dWx.append(dxd.t() @ u[g].view(T, D).float())
+        # the four GEMM-shaped gradients through x_proj / dt_proj.  bf16 activations: fp32 operands on the TF32 tensor
+        # path (10-bit mantissa >= the bf16 the forward used); fp32 activations: exact fp32.
+        tf32_prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = x0.dtype != torch.float32
+        try:
+            for g in range(G):
+                w = weights[g]
+                dd = ddelta[g].view(T, D)
+                dxd = d_x_dbl[g].view(T, E)
+                dxd[:, :R] = dd @ w.dt_proj_weight.float()                                   # d dt_low
+                halves = x_dbl[g].view(T, E)[:, :R].contiguous().view(torch.bfloat16)        # (T, 2R): [hi | lo]
+                dt_low = halves[:, :R].float() + halves[:, R:].float()
+                dWdt.append(dd.t() @ dt_low)
+                du[g].view(T, D).addmm_(dxd, w.x_proj_weight.float())                        # du += d_x_dbl . W_x
+                dWx.append(dxd.t() @ u[g].view(T, D).float())
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32_prev
         _cabi.check(lib.dm_mamba1_scan_bwd(C.byref(a), gr, 2, st), "dm_mamba1_scan_bwd(phase 2)")
         ops.LAUNCH_COUNTER["kernels"] += 2
         # scan order -> source-token order, summed over directions (adjoint of the CrossScan gather)
         dxz = []
+        inv = plan.inverse_table()          # (K, L_src) long: source token -> scanned position, or None (partial cover)
         for g in range(G):
-            acc = torch.zeros((B, Lsrc, 2 * D), **f32)
-            for k in range(K):
-                if plan.table is None or int(plan.table_host[k][0]) < 0:
-                    acc += d_xz_scan[g][:, k]
-                else:
-                    acc.index_add_(1, plan.table[k].long(), d_xz_scan[g][:, k])
+            if inv is not None:             # every direction is a full permutation: gather, no atomics
+                acc = None
+                for k in range(K):
+                    part = d_xz_scan[g][:, k] if inv[k] is None else d_xz_scan[g][:, k].index_select(1, inv[k])
+                    acc = part if acc is None else acc + part
+            else:
+                acc = torch.zeros((B, Lsrc, 2 * D), **f32)
+                for k in range(K):
+                    if plan.table is None or int(plan.table_host[k][0]) < 0:
+                        acc += d_xz_scan[g][:, k]
+                    else:
+                        acc.index_add_(1, plan.table[k].long(), d_xz_scan[g][:, k])
             dxz.append(acc.to(x0.dtype))
         grads = []
         for g in range(G):

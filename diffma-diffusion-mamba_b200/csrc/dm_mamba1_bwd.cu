@@ -357,11 +357,19 @@ extern "C" int dm_mamba1_scan_bwd(const dm_mamba1_args* a, const dm_mamba1_bwd_g
         const int n_units = n_seq * (p.D / 32);
         if (a->act_dtype == DM_F32) {
             const size_t bytes = sizeof(BwdSmem<float>);
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            static thread_local bool cfg = false;
+            if (!cfg) {
+                DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                cfg = true;
+            }
             m1_scan_bwd_kernel<float><<<n_units, 32, bytes, st>>>(p, n_units);
         } else {
             const size_t bytes = sizeof(BwdSmem<__nv_bfloat16>);
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            static thread_local bool cfg = false;
+            if (!cfg) {
+                DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                cfg = true;
+            }
             m1_scan_bwd_kernel<__nv_bfloat16><<<n_units, 32, bytes, st>>>(p, n_units);
         }
     } else {

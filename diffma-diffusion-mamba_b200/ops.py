@@ -76,6 +76,24 @@ class ScanPlan:
     def out_order(self) -> int:
         return _cabi.DM_OUT_SCAN_ORDER if self.layout == "stacked" else _cabi.DM_OUT_TOKEN_ORDER
 
+    def inverse_table(self):
+        """Per direction the inverse permutation (source token -> scanned position) as device int64 tensors (None for an
+        identity direction), or None altogether if some direction does not cover every source token exactly once."""
+        if self.seqlen != self.src_len:
+            return None
+        if getattr(self, "_inv", None) is None:
+            inv = []
+            for k in range(self.n_dir):
+                if self.table is None or int(self.table_host[k][0]) < 0:
+                    inv.append(None)
+                else:
+                    row = self.table_host[k].long()
+                    r = torch.empty_like(row)
+                    r[row] = torch.arange(row.numel())
+                    inv.append(r.to(self.table.device))
+            self._inv = inv
+        return self._inv
+
     def out_shape(self, batch: int, d: int):
         if self.layout == "concat":
             return (batch, self.src_len, self.n_dir, d)

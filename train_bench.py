@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--model", default="DiffMa-XL/4")
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -49,21 +50,50 @@ def main():
     model = net
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True)
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0, fused=True)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0, fused=True, capturable=not args.no_graph)
     patch = int(args.model.split("/")[1])
     L = (28 // patch) ** 2
     b = synth.synthetic_batch(args.batch, tokens=L, seed=100 + rank, device=device)
     kw = dict(y=b["y"], y2=b["y2"], w=b["w"])
     g = torch.Generator(device=device).manual_seed(rank)
+    t_buf = torch.zeros(args.batch, dtype=torch.long, device=device)
+    noise_buf = torch.zeros_like(b["x"])
+    loss_buf = torch.zeros((), device=device)
 
-    def step():
-        t = torch.randint(0, diffusion.num_timesteps, (args.batch,), device=device, generator=g)
+    def body():
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not args.fp32):
-            loss = diffusion.training_losses(model, b["x"], t, kw)["loss"].mean()
+            loss = diffusion.training_losses(model, b["x"], t_buf, kw, noise=noise_buf)["loss"].mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
-        return loss
+        loss_buf.copy_(loss.detach())
+
+    graph = None
+
+    def step():
+        # fresh timesteps / noise every step, drawn outside the graph into static buffers (train.py:243, q_sample)
+        t_buf.copy_(torch.randint(0, diffusion.num_timesteps, (args.batch,), device=device, generator=g))
+        noise_buf.normal_(generator=g)
+        if graph is not None:
+            graph.replay()
+        else:
+            body()
+        return loss_buf
+
+    if not args.no_graph:
+        # the whole step (forward, backward incl. dm_mamba1_scan_bwd, DDP all-reduce, fused AdamW) is one CUDA graph:
+        # the eager step is host-bound (~6000 launches for XL/4)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(11 if world > 1 else 3):
+                step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            body()
 
     for _ in range(max(3, args.warmup)):
         loss = step()
@@ -92,7 +122,7 @@ def main():
             "config": {"workload": f"{args.model} training step (fwd+bwd+{'DDP all-reduce+' if world > 1 else ''}AdamW), "
                                    f"L={L}, per-GPU batch {args.batch}", "global_batch": world * args.batch,
                        "grad_allreduce_mib": round(nparam * 4 / 2 ** 20, 1)},
-            "loss": round(float(loss.item()), 5), "gpu_launches": ops.LAUNCH_COUNTER["kernels"] - n0}), flush=True)
+            "loss": round(float(loss.item()), 5), "cuda_graph": graph is not None}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
