@@ -289,9 +289,11 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
     constexpr int tile_elems = (kTP2 + 3) * ld;
     T* Ws = reinterpret_cast<T*>(smem_raw);                  // [64][ld]
     T* Xs = Ws + kE * ld;                                    // [2][kTP2 + 3][ld]
+    int32_t* ord_s = reinterpret_cast<int32_t*>(Xs + 2 * tile_elems);   // [K][L] scan orders, loaded once per CTA
     const int L = p.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_per_seq = (L + kTP2 - 1) / kTP2;
+    const bool has_order = p.order != nullptr;
 
     auto decode = [&](int tile, int& g, int& b, int& k, int& j0) {
         const int seq = tile / tiles_per_seq;
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
         int g, b, k, j0;
         decode(tile, g, b, k, j0);
         const M1G& G = p.g[g];
-        const int32_t* ord = dir_order(p, k);
+        const int32_t* ord = has_order ? ord_s + k * L : nullptr;
         const T* x_base = static_cast<const T*>(G.xz) + static_cast<int64_t>(b) * G.xz_bs;
         T* dst = Xs + buf * tile_elems;
 #pragma unroll
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
                 if (j < 0) {
                     *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
                 } else if (j < L) {
-                    const int src = ord ? __ldg(ord + j) : j;
+                    const int src = ord ? ord[j] : j;
                     cp_async16(smem_u32(d), x_base + static_cast<int64_t>(src) * G.xz_ts + part * 8);
                 }
             }
@@ -342,8 +344,20 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
         cur_group = g;
     };
 
-    int tile = blockIdx.x;
-    if (tile >= n_tiles) return;
+    // contiguous tile range per CTA (consecutive tiles share their sequence: halo rows and order rows stay hot)
+    const int tile_lo = static_cast<int>(static_cast<int64_t>(blockIdx.x) * n_tiles / gridDim.x);
+    const int tile_hi = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * n_tiles / gridDim.x);
+    if (tile_lo >= tile_hi) return;
+    // scan orders of all directions -> shared memory (identity directions get the identity)
+    if (has_order) {
+        for (int i = tid; i < p.K * L; i += kP2Threads) {
+            const int kk = i / L, j = i - kk * L;
+            const int first = __ldg(p.order + static_cast<int64_t>(kk) * L);
+            ord_s[i] = first < 0 ? j : __ldg(p.order + i);
+        }
+        __syncthreads();
+    }
+    int tile = tile_lo;
     {
         int g, b, k, j0;
         decode(tile, g, b, k, j0);
@@ -352,12 +366,12 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
         cp_async_commit();
     }
     int buf = 0;
-    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    for (; tile < tile_hi; ++tile, buf ^= 1) {
         int g, b, k, j0;
         decode(tile, g, b, k, j0);
         const M1G& G = p.g[g];
-        const int next = tile + gridDim.x;
-        if (next < n_tiles) load_tile(next, buf ^ 1);
+        const int next = tile + 1;
+        if (next < tile_hi) load_tile(next, buf ^ 1);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
@@ -791,8 +805,8 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream) {
     // kernel P
     if (phases & 1) {
         const size_t ld = static_cast<size_t>(p.D) + 8;
-        const size_t bytes2 = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2;
-        if (!split && p.D == 1024) {                        // bf16, d_inner 1024: persistent kernel, W_x resident in shared memory
+        const size_t bytes2 = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2 + static_cast<size_t>(p.K) * p.L * 4;
+        if (!split && p.D == 1024 && bytes2 <= 227 * 1024) {                        // bf16, d_inner 1024: persistent kernel, W_x resident in shared memory
             static thread_local int n_sm = 0;
             if (n_sm == 0) {
                 int dev = 0;
