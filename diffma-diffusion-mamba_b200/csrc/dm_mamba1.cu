@@ -18,6 +18,8 @@
 // channel-sliced CTA can start scanning a token before every channel of it is convolved.  The scan is
 // MUFU-bound (16 ex2 per (b,d,l)), needs channel-sliced parallelism to fill 148 SMs, and the x_dbl
 // round trip is 256 B/token in L2 -- so the cut costs nothing measurable.
+#include <cstdlib>
+
 #include "dm_common.cuh"
 
 namespace dm {
@@ -483,6 +485,9 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
 // as packed fp32 pairs.  Two channels per lane halve the shared-memory (MIO) traffic for B/C per MUFU op and
 // give 32 independent ex2 per token, so ~10 resident warps per SM already saturate the MUFU pipe; at the
 // BASELINE shape (1536 warp-units) every unit is resident in a single wave on 148 SMs.
+#ifndef DM_CPL1_MINB
+#define DM_CPL1_MINB 20
+#endif
 // CPL = channels per lane (2 for the big shapes, 1 when there are too few warp-units to fill the SMs otherwise)
 template <typename T, int CPL> struct ScanSmem {
     static constexpr int kSC = 32 * CPL;     // channels per scan warp
@@ -573,7 +578,7 @@ __device__ __forceinline__ void ldmatrix_x4_u(uint32_t (&r)[4], uint32_t addr) {
 }
 
 template <typename T, int CPL>
-__global__ void __launch_bounds__(32, CPL == 2 ? 12 : 20) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
+__global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
     constexpr bool kSplit = sizeof(T) == 4;
     constexpr int kSC = 32 * CPL;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -849,7 +854,12 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream) {
         // two channels per lane (fewer shared-memory reads per MUFU op, 168 registers) when that still leaves >= 8
         // warps per SM; otherwise one channel per lane doubles the number of warp-units (small batches, config C5)
         const int units2 = n_seq * (p.D / 64);
-        if (units2 >= 8 * n_sm) {
+        static int force_cpl = -1;
+        if (force_cpl < 0) {
+            const char* e = getenv("DM_SCAN_CPL");
+            force_cpl = e ? atoi(e) : 0;
+        }
+        if (force_cpl == 2 || (force_cpl == 0 && units2 >= 8 * n_sm)) {
             m1_scan_kernel<T, 2><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
         } else {
             const int units1 = n_seq * (p.D / 32);
