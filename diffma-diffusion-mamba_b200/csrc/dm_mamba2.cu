@@ -11,7 +11,10 @@
 // straight out of the in-projection), so the whole op is one launch; the decay is one scalar per
 // (head, token), so the MUFU load is ~6 per (b,d,l) instead of Mamba-1's 20 and the kernel is bound by
 // the FP32 pipe.  (The chunked "SSD" tensor-core form is the planned next step; see DESIGN.md.)
+#include <cstdlib>
+
 #include "dm_common.cuh"
+#include "dm_mamba2_chunk.cuh"
 
 namespace dm {
 namespace {
@@ -246,8 +249,317 @@ __global__ void __launch_bounds__(32, 12) m2_ssd_kernel(const __grid_constant__ 
     }
 }
 
+// ---- tensor-core chunked SSD (bf16, headdim 64, d_state 16); see dm_mamba2_chunk.cuh -------------------------------
+__global__ void __launch_bounds__(ssd::kThreads, 4) m2_ssd_chunk_kernel(const __grid_constant__ M2P p) {
+    using namespace ssd;
+    using T = __nv_bfloat16;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane & 3, r4 = lane >> 2;
+    const int H = p.H, D = p.D, L = p.L;
+    const int head = blockIdx.x % H, seq = blockIdx.x / H;
+    const int k = seq % p.K, b = (seq / p.K) % p.B, g = seq / (p.K * p.B);
+    const M2G& G = p.g[g];
+    const int32_t* ord = dir_order(p, k);
+    const T* in_base = static_cast<const T*>(G.in) + static_cast<int64_t>(b) * G.in_bs;
+    T* out_base = static_cast<T*>(G.out) + static_cast<int64_t>(b) * G.out_bs + static_cast<int64_t>(k) * G.out_ds + head * P;
+    float* ssq = G.sumsq ? G.sumsq + static_cast<int64_t>(b) * G.ss_bs + static_cast<int64_t>(k) * G.ss_ds : nullptr;
+    const bool token_order = p.out_order == DM_OUT_TOKEN_ORDER;
+    const float A2 = __ldg(G.A + head) * kLog2e;
+    const float dtb = G.dt_bias ? __ldg(G.dt_bias + head) : 0.f;
+    const float Dh = G.D ? __ldg(G.D + head) : 0.f;
+    const int dt_off = 2 * D + 2 * NS + head;
+
+    // conv taps of this thread: x channel pair (2*(tid%32)) for 16 tokens, B|C channel pair (2*(tid%16)) for 8 tokens
+    const int xc = 2 * (tid & 31), xg = tid >> 5;
+    const int bc = 2 * (tid & 15), bg = tid >> 4;
+    float wx[2][kW], bx[2], wb[2][kW], bb[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(G.conv_w + static_cast<int64_t>(head * P + xc + i) * kW));
+        wx[i][0] = t.x; wx[i][1] = t.y; wx[i][2] = t.z; wx[i][3] = t.w;
+        bx[i] = G.conv_b ? __ldg(G.conv_b + head * P + xc + i) : 0.f;
+        t = __ldg(reinterpret_cast<const float4*>(G.conv_w + static_cast<int64_t>(D + bc + i) * kW));
+        wb[i][0] = t.x; wb[i][1] = t.y; wb[i][2] = t.z; wb[i][3] = t.w;
+        bb[i] = G.conv_b ? __ldg(G.conv_b + D + bc + i) : 0.f;
+    }
+
+    float stacc[2][4];                               // state[n][p] of this warp's 16 channels, fp32
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) stacc[i][e] = 0.f;
+
+    const int n_chunks = (L + Q - 1) / Q;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int j0 = c * Q, nv = min(Q, L - j0);
+        // ---- (a) gather the chunk's rows (scan order) ----
+        for (int s = tid; s < (Q + 3) * 8; s += kThreads) {
+            const int r = s >> 3, part = s & 7, j = j0 - 3 + r;
+            T* d = &S.xraw[r][part * 8];
+            if (j < 0 || j >= L) {
+                *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                const int src = ord ? __ldg(ord + j) : j;
+                cp_async16(smem_u32(d), in_base + static_cast<int64_t>(src) * G.in_ts + D + head * P + part * 8);
+            }
+        }
+        for (int s = tid; s < (Q + 3) * 4; s += kThreads) {
+            const int r = s >> 2, part = s & 3, j = j0 - 3 + r;
+            T* d = &S.bcraw[r][part * 8];
+            if (j < 0 || j >= L) {
+                *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                const int src = ord ? __ldg(ord + j) : j;
+                cp_async16(smem_u32(d), in_base + static_cast<int64_t>(src) * G.in_ts + 2 * D + part * 8);
+            }
+        }
+        for (int s = tid; s < Q * 8; s += kThreads) {
+            const int r = s >> 3, part = s & 7, j = j0 + r;
+            T* d = &S.zs[r][part * 8];
+            if (j >= L) {
+                *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+                if (part == 0) S.rows[r] = 0;
+            } else {
+                const int src = ord ? __ldg(ord + j) : j;
+                if (part == 0) S.rows[r] = token_order ? src : j;
+                cp_async16(smem_u32(d), in_base + static_cast<int64_t>(src) * G.in_ts + head * P + part * 8);
+            }
+        }
+        float dt_raw[2] = {0.f, 0.f};
+        bool dt_ok[2] = {false, false};
+        if (tid < 32) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int j = j0 + 2 * tid + i;
+                if (j < L) {
+                    const int src = ord ? __ldg(ord + j) : j;
+                    dt_raw[i] = to_f32<T>(in_base[static_cast<int64_t>(src) * G.in_ts + dt_off]);
+                    dt_ok[i] = true;
+                }
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+
+        // ---- (b) conv + SiLU -> X, B, C ; dt, cumulative log-decay ----
+        {
+            float w0[2], w1[2], w2[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                w0[i] = to_f32<T>(S.xraw[16 * xg + 0][xc + i]);
+                w1[i] = to_f32<T>(S.xraw[16 * xg + 1][xc + i]);
+                w2[i] = to_f32<T>(S.xraw[16 * xg + 2][xc + i]);
+            }
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int jj = 16 * xg + t;
+                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&S.xraw[jj + 3][xc]);
+                const float xn[2] = {__low2float(v), __high2float(v)};
+                float o[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float acc = bx[i];
+                    acc = fmaf(wx[i][0], w0[i], acc); acc = fmaf(wx[i][1], w1[i], acc);
+                    acc = fmaf(wx[i][2], w2[i], acc); acc = fmaf(wx[i][3], xn[i], acc);
+                    o[i] = silu_t(acc);
+                    w0[i] = w1[i]; w1[i] = w2[i]; w2[i] = xn[i];
+                }
+                *reinterpret_cast<uint32_t*>(&S.xs[jj][xc]) = pk(o[0], o[1]);
+            }
+        }
+        {
+            float w0[2], w1[2], w2[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                w0[i] = to_f32<T>(S.bcraw[8 * bg + 0][bc + i]);
+                w1[i] = to_f32<T>(S.bcraw[8 * bg + 1][bc + i]);
+                w2[i] = to_f32<T>(S.bcraw[8 * bg + 2][bc + i]);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int jj = 8 * bg + t;
+                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&S.bcraw[jj + 3][bc]);
+                const float xn[2] = {__low2float(v), __high2float(v)};
+                float o[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float acc = bb[i];
+                    acc = fmaf(wb[i][0], w0[i], acc); acc = fmaf(wb[i][1], w1[i], acc);
+                    acc = fmaf(wb[i][2], w2[i], acc); acc = fmaf(wb[i][3], xn[i], acc);
+                    o[i] = silu_fast(acc);
+                    w0[i] = w1[i]; w1[i] = w2[i]; w2[i] = xn[i];
+                }
+                if (bc < NS) *reinterpret_cast<uint32_t*>(&S.bs[jj][bc]) = pk(o[0], o[1]);
+                else *reinterpret_cast<uint32_t*>(&S.cs[jj][bc - NS]) = pk(o[0], o[1]);
+            }
+        }
+        if (tid < 32) {          // tokens 2*tid, 2*tid+1: dt, inclusive cumsum of dt*A*log2(e)
+            const float d0 = dt_ok[0] ? softplus_f(dt_raw[0] + dtb) : 0.f;
+            const float d1 = dt_ok[1] ? softplus_f(dt_raw[1] + dtb) : 0.f;
+            const float s0 = d0 * A2, s1 = s0 + d1 * A2;
+            float incl = s1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const float excl = incl - s1;
+            S.cum[2 * tid] = excl + s0; S.cum[2 * tid + 1] = excl + s1;
+            S.dtv[2 * tid] = d0; S.dtv[2 * tid + 1] = d1;
+        }
+        __syncthreads();
+
+        // ---- (c)-(g) this warp's 16 chunk rows ----
+        {
+            const int i0 = 16 * warp + r4, i1 = i0 + 8;
+            const float ci0 = S.cum[i0], ci1 = S.cum[i1];
+            uint32_t a_c[4];
+            ldsm_x4(a_c, smem_u32(&S.cs[16 * warp + (lane & 15)][(lane >> 4) * 8]));
+            float y[8][4];
+#pragma unroll
+            for (int pt = 0; pt < 8; ++pt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) y[pt][e] = 0.f;
+            for (int kk = 0; kk <= warp; ++kk) {
+                uint32_t bfr[4];
+                ldsm_x4(bfr, smem_u32(&S.bs[16 * kk + (lane & 7) + ((lane >> 4) & 1) * 8][((lane >> 3) & 1) * 8]));
+                float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+                mma16816(s0, a_c, bfr[0], bfr[1]);
+                mma16816(s1, a_c, bfr[2], bfr[3]);
+                const int ja = 16 * kk + 2 * q, jb = ja + 8;
+                const float2 cja = *reinterpret_cast<const float2*>(&S.cum[ja]), cjb = *reinterpret_cast<const float2*>(&S.cum[jb]);
+                const float2 dja = *reinterpret_cast<const float2*>(&S.dtv[ja]), djb = *reinterpret_cast<const float2*>(&S.dtv[jb]);
+                auto mk = [&](float s, float ci, float cj, float dj, int i, int j) {
+                    return (j <= i) ? s * ex2_approx(ci - cj) * dj : 0.f;
+                };
+                uint32_t am[4];
+                am[0] = pk(mk(s0[0], ci0, cja.x, dja.x, i0, ja), mk(s0[1], ci0, cja.y, dja.y, i0, ja + 1));
+                am[1] = pk(mk(s0[2], ci1, cja.x, dja.x, i1, ja), mk(s0[3], ci1, cja.y, dja.y, i1, ja + 1));
+                am[2] = pk(mk(s1[0], ci0, cjb.x, djb.x, i0, jb), mk(s1[1], ci0, cjb.y, djb.y, i0, jb + 1));
+                am[3] = pk(mk(s1[2], ci1, cjb.x, djb.x, i1, jb), mk(s1[3], ci1, cjb.y, djb.y, i1, jb + 1));
+#pragma unroll
+                for (int pt2 = 0; pt2 < 4; ++pt2) {
+                    uint32_t xb[4];
+                    ldsm_x4_t(xb, smem_u32(&S.xs[16 * kk + (lane & 15)][pt2 * 16 + (lane >> 4) * 8]));
+                    mma16816(y[2 * pt2], am, xb[0], xb[1]);
+                    mma16816(y[2 * pt2 + 1], am, xb[2], xb[3]);
+                }
+            }
+            if (c > 0) {                              // contribution of the state carried in from earlier chunks
+                const float e0 = ex2_approx(ci0), e1 = ex2_approx(ci1);
+#pragma unroll
+                for (int pt2 = 0; pt2 < 4; ++pt2) {
+                    uint32_t sb[4];
+                    ldsm_x4_t(sb, smem_u32(&S.st[lane & 15][pt2 * 16 + (lane >> 4) * 8]));
+                    float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma16816(t0, a_c, sb[0], sb[1]);
+                    mma16816(t1, a_c, sb[2], sb[3]);
+                    y[2 * pt2][0] = fmaf(e0, t0[0], y[2 * pt2][0]); y[2 * pt2][1] = fmaf(e0, t0[1], y[2 * pt2][1]);
+                    y[2 * pt2][2] = fmaf(e1, t0[2], y[2 * pt2][2]); y[2 * pt2][3] = fmaf(e1, t0[3], y[2 * pt2][3]);
+                    y[2 * pt2 + 1][0] = fmaf(e0, t1[0], y[2 * pt2 + 1][0]); y[2 * pt2 + 1][1] = fmaf(e0, t1[1], y[2 * pt2 + 1][1]);
+                    y[2 * pt2 + 1][2] = fmaf(e1, t1[2], y[2 * pt2 + 1][2]); y[2 * pt2 + 1][3] = fmaf(e1, t1[3], y[2 * pt2 + 1][3]);
+                }
+            }
+            // epilogue: D skip, gate, store, sum of squares
+            float sq0 = 0.f, sq1 = 0.f;
+            const int64_t ro0 = static_cast<int64_t>(S.rows[i0]) * G.out_ts, ro1 = static_cast<int64_t>(S.rows[i1]) * G.out_ts;
+#pragma unroll
+            for (int pt = 0; pt < 8; ++pt) {
+                const int pc = pt * 8 + 2 * q;
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int i = hrow ? i1 : i0;
+                    const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(&S.xs[i][pc]);
+                    float v0 = fmaf(Dh, __low2float(xv), y[pt][2 * hrow]), v1 = fmaf(Dh, __high2float(xv), y[pt][2 * hrow + 1]);
+                    if (p.gate) {
+                        const __nv_bfloat162 zv = *reinterpret_cast<const __nv_bfloat162*>(&S.zs[i][pc]);
+                        v0 *= silu_t(__low2float(zv));
+                        v1 *= silu_t(__high2float(zv));
+                    }
+                    if (i < nv) {
+                        *reinterpret_cast<uint32_t*>(out_base + (hrow ? ro1 : ro0) + pc) = pk(v0, v1);
+                        if (hrow) sq1 = fmaf(v0, v0, fmaf(v1, v1, sq1)); else sq0 = fmaf(v0, v0, fmaf(v1, v1, sq0));
+                    }
+                }
+            }
+            if (ssq) {
+                sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
+                sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2);
+                if (q == 0) {
+                    if (i0 < nv) atomicAdd(ssq + S.rows[i0], sq0);
+                    if (i1 < nv) atomicAdd(ssq + S.rows[i1], sq1);
+                }
+            }
+        }
+        if (c + 1 == n_chunks) break;
+        __syncthreads();                                // every warp is done reading the old state copy
+
+        // ---- (h) state update: State = exp(cum_last) State + (B o w)^T X, warp owns channels [16w, 16w+16) ----
+        {
+            const float wl = S.cum[Q - 1];
+            float sn[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sn[i][e] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < Q / 16; ++kk) {
+                uint32_t ab[4];
+                ldsm_x4_t(ab, smem_u32(&S.bs[16 * kk + (lane & 7) + ((lane >> 4) & 1) * 8][((lane >> 3) & 1) * 8]));
+                const int ja = 16 * kk + 2 * q, jb = ja + 8;
+                const float2 cja = *reinterpret_cast<const float2*>(&S.cum[ja]), cjb = *reinterpret_cast<const float2*>(&S.cum[jb]);
+                const float2 dja = *reinterpret_cast<const float2*>(&S.dtv[ja]), djb = *reinterpret_cast<const float2*>(&S.dtv[jb]);
+                const __nv_bfloat162 wa = __floats2bfloat162_rn(ex2_approx(wl - cja.x) * dja.x, ex2_approx(wl - cja.y) * dja.y);
+                const __nv_bfloat162 wbv = __floats2bfloat162_rn(ex2_approx(wl - cjb.x) * djb.x, ex2_approx(wl - cjb.y) * djb.y);
+                auto scale = [](uint32_t v, __nv_bfloat162 w) {
+                    __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&v), w);
+                    return *reinterpret_cast<uint32_t*>(&r);
+                };
+                ab[0] = scale(ab[0], wa); ab[1] = scale(ab[1], wa); ab[2] = scale(ab[2], wbv); ab[3] = scale(ab[3], wbv);
+                uint32_t xb[4];
+                ldsm_x4_t(xb, smem_u32(&S.xs[16 * kk + (lane & 15)][16 * warp + (lane >> 4) * 8]));
+                mma16816(sn[0], ab, xb[0], xb[1]);
+                mma16816(sn[1], ab, xb[2], xb[3]);
+            }
+            const float el = ex2_approx(wl);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) stacc[i][e] = fmaf(el, stacc[i][e], sn[i][e]);
+                const int pc = 16 * warp + i * 8 + 2 * q;
+                *reinterpret_cast<uint32_t*>(&S.st[r4][pc]) = pk(stacc[i][0], stacc[i][1]);
+                *reinterpret_cast<uint32_t*>(&S.st[r4 + 8][pc]) = pk(stacc[i][2], stacc[i][3]);
+            }
+        }
+        __syncthreads();                                // new state visible; chunk buffers free for the next gather
+    }
+}
+
 template <typename T>
 int launch_m2(const M2P& p, cudaStream_t stream) {
+    if constexpr (sizeof(T) == 2) {
+        // bf16, headdim 64: the chunked tensor-core form (DM_M2_CHUNK=0 forces the sequential kernel)
+        static int use_chunk = -1;
+        if (use_chunk < 0) {
+            const char* e = getenv("DM_M2_CHUNK");
+            use_chunk = e ? atoi(e) : 1;
+        }
+        if (use_chunk && p.P == ssd::P) {
+            static thread_local bool cfg = false;
+            if (!cfg) {
+                DM_CUDA_TRY(cudaFuncSetAttribute(m2_ssd_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(sizeof(ssd::Smem))));
+                DM_CUDA_TRY(cudaFuncSetAttribute(m2_ssd_chunk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                cfg = true;
+            }
+            const int units = p.n_groups * p.B * p.K * p.H;
+            m2_ssd_chunk_kernel<<<units, ssd::kThreads, sizeof(ssd::Smem), stream>>>(p);
+            DM_CUDA_TRY(cudaGetLastError());
+            return DM_OK;
+        }
+    }
     const int n_units = p.n_groups * p.B * p.K * (p.D / kSC);
     const size_t bytes = sizeof(SsdSmem<T>);
     static thread_local bool configured = false;

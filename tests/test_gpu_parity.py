@@ -262,3 +262,32 @@ def test_p_sample_update_kernel_matches_reference_golden(dev):
         out = d.p_sample(fake_model, x.to(dev), t.to(dev), clip_denoised=False, noise=n.to(dev))
         np.testing.assert_allclose(out["sample"].cpu().numpy(), g[f"{tag}_p_sample"], rtol=2e-5, atol=2e-5)
         np.testing.assert_allclose(out["pred_xstart"].cpu().numpy(), g[f"{tag}_pmv_pred_xstart"], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("B,L", [(2, 196), (1, 49), (2, 64), (1, 130), (1, 784), (3, 5)])
+def test_mamba2_combined_bf16_chunked_vs_oracle(dev, B, L):
+    """mamba_split_conv1d_scan_combined in bf16 (tensor-core chunked SSD kernel: 64-token chunks, so L = 49 / 64 / 130 /
+    196 / 784 cover partial, exact, multi-chunk and ragged-tail cases) vs the fp32 oracle on the same rounded inputs."""
+    from diffma_b200 import ops
+    from oracle import ref_ops
+    g = torch.Generator().manual_seed(100 + L)
+    d_in, N, H, P = 1024, 16, 16, 64
+    zx = torch.randn(B, L, 2 * d_in + 2 * N + H, generator=g)
+    zx[..., -H:] = zx[..., -H:] - 2.0                                # dt pre-activations around softplus ~ 0.1
+    conv_w = torch.randn(d_in + 2 * N, 4, generator=g) * 0.4
+    conv_b = torch.randn(d_in + 2 * N, generator=g) * 0.1
+    dt_bias = torch.randn(H, generator=g) * 0.5
+    A = -(1 + 15 * torch.rand(H, generator=g))
+    Dp = 1 + 0.1 * torch.randn(H, generator=g)
+    nw = 1 + 0.1 * torch.randn(d_in, generator=g)
+    wo = torch.randn(512, d_in, generator=g) / d_in ** 0.5
+    zb, wob = zx.bfloat16(), wo.bfloat16()
+    ref = ref_ops.mamba_split_conv1d_scan_ref(zb.float(), conv_w, conv_b, dt_bias, A, Dp, 256, rmsnorm_weight=nw,
+                                              rmsnorm_eps=1e-5, outproj_weight=wob.float(), headdim=P, ngroups=1,
+                                              norm_before_gate=False)
+    c = lambda t: t.to(dev)
+    out = ops.mamba_split_conv1d_scan_combined(c(zb), c(conv_w), c(conv_b), c(dt_bias), c(A), c(Dp), 256,
+                                               rmsnorm_weight=c(nw), rmsnorm_eps=1e-5, outproj_weight=c(wob), headdim=P,
+                                               ngroups=1, norm_before_gate=False)
+    assert out.dtype == torch.bfloat16 and out.shape == (B, L, 512)
+    torch.testing.assert_close(out.float().cpu(), ref, **BF16_TOL)

@@ -31,6 +31,10 @@ def main():
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # DDP's NCCL all-reduce inside a whole-step capture deadlocked on this stack (torch 2.11 / NCCL 2.28): multi-GPU
+        # steps are launched eagerly (host-bound); the single-GPU step is one CUDA graph
+        args.no_graph = True
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -48,8 +52,14 @@ def main():
     net = net.to(device).train()
     ema = None
     model = net
+    side = torch.cuda.Stream(device=device)
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True)
+        # DDP is built (and warmed up, below) on the side stream the graph capture will run on: its AccumulateGrad /
+        # bucket hooks remember the stream they were created under (torch's DDP + CUDA graphs recipe)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True)
+        torch.cuda.current_stream(device).wait_stream(side)
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0, fused=True, capturable=not args.no_graph)
     patch = int(args.model.split("/")[1])
     L = (28 // patch) ** 2
@@ -83,7 +93,6 @@ def main():
     if not args.no_graph:
         # the whole step (forward, backward incl. dm_mamba1_scan_bwd, DDP all-reduce, fused AdamW) is one CUDA graph:
         # the eager step is host-bound (~6000 launches for XL/4)
-        side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             for _ in range(11 if world > 1 else 3):
@@ -92,8 +101,15 @@ def main():
         torch.cuda.synchronize(device)
         graph = torch.cuda.CUDAGraph()
         opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(graph):
-            body()
+        try:
+            with torch.cuda.graph(graph, stream=side):
+                body()
+        except RuntimeError as e:       # capture refused (e.g. a DDP/NCCL combination that cannot be captured): run eagerly
+            if rank == 0:
+                print(f"train_bench: CUDA-graph capture failed ({str(e).splitlines()[0]}); falling back to eager steps",
+                      file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize(device)
 
     for _ in range(max(3, args.warmup)):
         loss = step()
