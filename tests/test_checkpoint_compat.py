@@ -1,0 +1,64 @@
+"""Checkpoint compatibility (SURVEY.md section 8f rank 4, section 5 'checkpoint / resume'): state dicts written by the
+reference load into this package's modules unchanged.  Needs the reference checkout (build container only)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+CKPT = os.path.join(REF, "pretrain_ct_vision_embedder", "brain_patch_size_2.pt")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(CKPT), reason="reference checkout with shipped checkpoints not present")
+
+
+def _load():
+    torch.serialization.add_safe_globals([argparse.Namespace])
+    return torch.load(CKPT, map_location="cpu", weights_only=True)
+
+
+def test_shipped_ct_embedder_checkpoint_loads_strict_and_matches_reference_forward():
+    """The CT soft-mask embedder shipped with the reference ({model, ema, opt, args}; train_embedder.py) loads with
+    strict=True into diffma_b200.ct_encoder.CT_Encoder and produces the reference module's outputs."""
+    from diffma_b200.ct_encoder import CT_Encoder
+    ck = _load()
+    assert {"model", "ema"} <= set(ck)
+    ours = CT_Encoder(img_size=28, patch_size=2, in_channels=4, embed_dim=512, contain_mask_token=True).eval()
+    missing = ours.load_state_dict(ck["ema"], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    sys.path.insert(0, REF)
+    try:
+        from block.CT_encoder import CT_Encoder as RefEnc
+    finally:
+        sys.path.remove(REF)
+    ref = RefEnc(img_size=28, patch_size=2, in_channels=4, embed_dim=512, contain_mask_token=True).eval()
+    ref.load_state_dict(ck["ema"], strict=True)
+    x = torch.randn(3, 4, 28, 28, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        w0, y0 = ref(x)
+        w1, y1 = ours(x)
+    np.testing.assert_allclose(w1.numpy(), w0.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(y1.numpy(), y0.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_reference_model_state_dict_loads_into_mirror():
+    """A state dict produced by the reference's own DiffMa (built over the product shims) loads with strict=True into
+    diffma_b200.model.DiffMa for both mixer generations (keys AND shapes)."""
+    import subprocess
+    code = (
+        "import sys, torch\n"
+        "import model as R\n"
+        "from diffma_b200 import model as M\n"
+        "for m2 in (False, True):\n"
+        "    ref = R.DiffMa_models['DiffMa-S/2'](input_size=28, dt_rank=16, d_state=16, use_mamba2=m2)\n"
+        "    ours = M.DiffMa_models['DiffMa-S/2'](input_size=28, dt_rank=16, d_state=16, use_mamba2=m2)\n"
+        "    res = ours.load_state_dict(ref.state_dict(), strict=True)\n"
+        "    assert not res.missing_keys and not res.unexpected_keys\n"
+        "print('ok')\n")
+    shims = os.path.join(ROOT, "diffma-diffusion-mamba_b200", "shims")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([shims, ROOT, REF]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]

@@ -291,3 +291,27 @@ def test_mamba2_combined_bf16_chunked_vs_oracle(dev, B, L):
                                                ngroups=1, norm_before_gate=False)
     assert out.dtype == torch.bfloat16 and out.shape == (B, L, 512)
     torch.testing.assert_close(out.float().cpu(), ref, **BF16_TOL)
+
+
+def test_graphed_sampler_matches_eager_steps(dev, monkeypatch):
+    """GraphedSampler (one CUDA graph per p_sample step, pooled y2, in-graph timestep decrement) reproduces three eager
+    ``p_sample`` steps when the Gaussian noise is replaced by a fixed tensor."""
+    from diffma_b200 import create_model_and_diffusion, synth
+    from diffma_b200.diffusion import GraphedSampler
+    monkeypatch.setattr(torch, "randn_like", lambda t, **kw: torch.full_like(t, 0.25))
+    torch.manual_seed(0)
+    net, diffusion = create_model_and_diffusion("DiffMa-S/2", respacing="250")
+    synth.fill_trained_like_(net, seed=11)
+    net = net.to(dev).eval()
+    b = synth.synthetic_batch(2, tokens=196, seed=4, device=dev)
+    kw = dict(y=b["y"], y2=b["y2"], w=b["w"])
+    x = b["x"].clone()
+    for i in range(3):
+        t = torch.full((2,), diffusion.num_timesteps - 1 - i, device=dev, dtype=torch.long)
+        x = diffusion.p_sample(net, x, t, clip_denoised=False, model_kwargs=kw)["sample"]
+    s = GraphedSampler(diffusion, net, tuple(b["x"].shape), kw, dev, pool_y2=True)
+    s.reset(b["x"])
+    for _ in range(3):
+        s.step()
+    torch.testing.assert_close(s.x, x, rtol=1e-4, atol=1e-4)
+    assert s.kernels_per_step > 0          # the step really launches this package's kernels
