@@ -349,19 +349,27 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host.values() if v is not host["t"]) + t_host.numel() * 8
     d2h = out_host.numel() * 4
 
-    def e2e_step():
-        sampler.load(host["x"], t_host, {"y": host["y"], "y2": host["y2"], "w": host["w"]})   # pinned H2D, async
-        sampler.step()
-        out_host.copy_(sampler.x, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()
+    kw_host = {"y": host["y"], "y2": host["y2"], "w": host["w"]}
+    main = torch.cuda.current_stream(device)
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_run(n):
+        # every step: H2D of that step's pinned inputs (double buffered: the copy of step i+1 travels on a copy stream
+        # while step i computes), the step, D2H of the step's sample, host sync on the result
+        sampler.prefetch(0, host["x"], t_host, kw_host)
+        for i in range(n):
+            s = i & 1
+            sampler.load_staged(s)
+            if i + 1 < n:
+                sampler.prefetch(1 - s, host["x"], t_host, kw_host)
+            sampler.step()
+            out_host.copy_(sampler.x, non_blocking=True)
+            main.synchronize()
+
+    e2e_run(3)
     barrier(world)
     torch.cuda.synchronize(device)
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     e1.record()
     torch.cuda.synchronize(device)
     barrier(world)

@@ -342,6 +342,39 @@ class GraphedSampler:
             self.kw[k].copy_(v, non_blocking=True)
         self._pool()
 
+    # ---- double-buffered input streaming: the next step's H2D overlaps the current step's kernels ------------
+    def prefetch(self, slot: int, x_host: torch.Tensor, t_host: torch.Tensor, kw_host: dict):
+        """Start the asynchronous H2D of one step's (pinned) host inputs into staging slot 0/1 on a copy stream."""
+        dev = self.x.device
+        if not hasattr(self, "_stage"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [dict(x=torch.empty_like(self.x), t=torch.empty_like(self.t),
+                                **{k: torch.empty_like(v) for k, v in self.kw.items()}) for _ in range(2)]
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._free = [torch.cuda.Event() for _ in range(2)]
+            for e in self._free:
+                e.record(torch.cuda.current_stream(dev))
+        st = self._stage[slot]
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._free[slot])          # the slot's previous contents have been consumed
+            st["x"].copy_(x_host, non_blocking=True)
+            st["t"].copy_(t_host, non_blocking=True)
+            for k, v in kw_host.items():
+                st[k].copy_(v, non_blocking=True)
+            self._ready[slot].record(self._copy_stream)
+
+    def load_staged(self, slot: int):
+        """Make staging slot ``slot`` the current step's inputs (device-to-device, on the compute stream)."""
+        main = torch.cuda.current_stream(self.x.device)
+        main.wait_event(self._ready[slot])
+        st = self._stage[slot]
+        self.x.copy_(st["x"])
+        self.t.copy_(st["t"])
+        for k in self.kw:
+            self.kw[k].copy_(st[k])
+        self._free[slot].record(main)
+        self._pool()
+
     def _pool(self):
         if self.y2_pooled is not None:
             torch.mean(self.kw["y2"], dim=1, out=self.y2_pooled)
