@@ -3,7 +3,12 @@
 ``Mamba1ScanFn`` runs the same C-ABI forward as inference, keeps the intermediates (u, x_dbl) and implements upstream
 ``MambaInnerFn.backward`` (minus the out-projection, which stays a torch GEMM) on ``dm_mamba1_scan_bwd``: reverse scan
 kernel -> four small library GEMMs (through x_proj / dt_proj) -> conv backward kernel -> un-permute + sum directions.
-``Mamba2SsdFn`` has no backward kernel yet and raises instead of silently falling back.
+``Mamba2SsdFn`` differentiates ``dm_mamba2_ssd_fwd`` (upstream ``MambaSplitConv1dScanCombinedFn.backward`` minus the
+RMSNorm scale and the out-projection, which stay torch ops) through the SAME reverse-scan kernel: the SSD recurrence
+is the S6 recurrence with ``A[d, n] = A_head(d)`` and ``delta[d] = dt_head(d)`` (self-consistency (2)),
+so the Mamba-2 operands are laid out as a Mamba-1 problem (dt as the dt_low slots + a one-hot dt_proj), the kernel
+returns per-channel gradients and the host reduces them per head.  Correct-first: it spends 16 exps per
+(token, channel) where a dedicated SSD backward needs one per (token, head).
 """
 from __future__ import annotations
 
@@ -24,6 +29,36 @@ def flatten_weights(weights):
 
 def _det(t):
     return None if t is None else t.detach()
+
+
+def gather_scan_order(t: torch.Tensor, plan) -> torch.Tensor:
+    """(B, L_src, C) -> (B, K, L, C): row j of direction k = source token plan.table[k, j] (the CrossScan gather)."""
+    rows = []
+    for k in range(plan.n_dir):
+        if plan.table is None or int(plan.table_host[k][0]) < 0:
+            rows.append(t)
+        else:
+            rows.append(t.index_select(1, plan.table[k].long()))
+    return torch.stack(rows, 1)
+
+
+def scan_to_token_sum(g_scan: torch.Tensor, plan) -> torch.Tensor:
+    """Adjoint of ``gather_scan_order``: (B, K, L, C) gradients in scan order -> (B, L_src, C), summed over directions."""
+    B, K = g_scan.shape[:2]
+    inv = plan.inverse_table()          # (K, L_src) long: source token -> scanned position, or None (partial cover)
+    if inv is not None:                 # every direction is a full permutation: gather, no atomics
+        acc = None
+        for k in range(K):
+            part = g_scan[:, k] if inv[k] is None else g_scan[:, k].index_select(1, inv[k])
+            acc = part if acc is None else acc + part
+        return acc
+    acc = torch.zeros((B, plan.src_len, g_scan.shape[-1]), dtype=g_scan.dtype, device=g_scan.device)
+    for k in range(K):
+        if plan.table is None or int(plan.table_host[k][0]) < 0:
+            acc += g_scan[:, k]
+        else:
+            acc.index_add_(1, plan.table[k].long(), g_scan[:, k])
+    return acc
 
 
 class Mamba1ScanFn(torch.autograd.Function):
@@ -105,23 +140,7 @@ class Mamba1ScanFn(torch.autograd.Function):
             torch.backends.cuda.matmul.allow_tf32 = tf32_prev
         _cabi.check(lib.dm_mamba1_scan_bwd(C.byref(a), gr, 2, st), "dm_mamba1_scan_bwd(phase 2)")
         ops.LAUNCH_COUNTER["kernels"] += 2
-        # scan order -> source-token order, summed over directions (adjoint of the CrossScan gather)
-        dxz = []
-        inv = plan.inverse_table()          # (K, L_src) long: source token -> scanned position, or None (partial cover)
-        for g in range(G):
-            if inv is not None:             # every direction is a full permutation: gather, no atomics
-                acc = None
-                for k in range(K):
-                    part = d_xz_scan[g][:, k] if inv[k] is None else d_xz_scan[g][:, k].index_select(1, inv[k])
-                    acc = part if acc is None else acc + part
-            else:
-                acc = torch.zeros((B, Lsrc, 2 * D), **f32)
-                for k in range(K):
-                    if plan.table is None or int(plan.table_host[k][0]) < 0:
-                        acc += d_xz_scan[g][:, k]
-                    else:
-                        acc.index_add_(1, plan.table[k].long(), d_xz_scan[g][:, k])
-            dxz.append(acc.to(x0.dtype))
+        dxz = [scan_to_token_sum(d_xz_scan[g], plan).to(x0.dtype) for g in range(G)]
         grads = []
         for g in range(G):
             w = weights[g]
@@ -133,6 +152,133 @@ class Mamba1ScanFn(torch.autograd.Function):
         return (None, None, *dxz, *grads)
 
 
+def s6_backward_cuda(u, z_src, dt_raw, Bm, Cm, A_h, D_h, dtb_h, dv, plan, nheads):
+    """Reverse scan of the SSD recurrence on ``dm_mamba1_scan_bwd`` (phase 1), all groups in one launch.
+
+    u (G,B,K,L,D) act dtype = silu(conv(x)) in scan order; z_src[g] (B,L_src,D) act; dt_raw (G,B,K,L,H) fp32 (before
+    bias / softplus); Bm, Cm (G,B,K,L,N) fp32; A_h / D_h / dtb_h [g] (H,) fp32 (D_h, dtb_h may be None); dv (G,) +
+    plan.out_shape act dtype = gradient of the gated output.  Returns per-CHANNEL fp32 gradients in scan order:
+    dz, du, ddelta (G,B,K,L,D); dB, dC (G,B,K,L,N); dA (G,D,N); dD, ddtb (G,D).
+    """
+    G, B, K, L, D = u.shape
+    H, N = nheads, Bm.shape[-1]
+    P, R = D // H, 32
+    if H > R or N != 16:
+        raise NotImplementedError("diffma_b200: Mamba-2 backward needs nheads <= 32 and d_state == 16 (all DiffMa uses)")
+    dev, act = u.device, u.dtype
+    f32 = dict(dtype=torch.float32, device=dev)
+    # x_dbl rows as the Mamba-1 kernels read them: [dt_low hi: 32 bf16 | dt_low lo: 32 bf16 | B: 16 f32 | C: 16 f32]
+    xd_bf = torch.zeros((G, B, K, L, 4 * R), dtype=torch.bfloat16, device=dev)
+    hi = dt_raw.to(torch.bfloat16)
+    xd_bf[..., :H] = hi
+    xd_bf[..., R:R + H] = (dt_raw - hi.float()).to(torch.bfloat16)
+    x_dbl = xd_bf.view(torch.float32)                                   # (G,B,K,L,64)
+    x_dbl[..., R:R + N] = Bm
+    x_dbl[..., R + N:] = Cm
+    head = torch.arange(D, device=dev) // P
+    onehot = torch.zeros((D, R), **f32)
+    onehot[torch.arange(D, device=dev), head] = 1.0
+    xz, weights = [], []
+    for g in range(G):
+        t = torch.zeros((B, plan.src_len, 2 * D), dtype=act, device=dev)
+        t[..., D:] = z_src[g]
+        xz.append(t)
+        weights.append(ops.Mamba1Weights(
+            conv_weight=torch.zeros((D, 4), **f32), conv_bias=None,
+            x_proj_weight=torch.zeros((R + 2 * N, D), dtype=act, device=dev), dt_proj_weight=onehot.to(act),
+            dt_bias=None if dtb_h[g] is None else dtb_h[g].float()[head].contiguous(),
+            A=A_h[g].float()[head].unsqueeze(1).expand(D, N).contiguous(),
+            D=None if D_h[g] is None else D_h[g].float()[head].contiguous()))
+    a, _ = ops.mamba1_args(xz, weights, plan, bufs=(dv.contiguous(), u.contiguous(), x_dbl))
+    nch = (L + 7) // 8
+    d_xz_scan = torch.zeros((G, B, K, L, 2 * D), **f32)
+    du = torch.empty((G, B, K, L, D), **f32)
+    ddelta = torch.empty((G, B, K, L, D), **f32)
+    d_x_dbl = torch.zeros((G, B, K, L, R + 2 * N), **f32)
+    dA = torch.zeros((G, D, N), **f32)
+    dD = torch.zeros((G, D), **f32)
+    ddtb = torch.zeros((G, D), **f32)
+    ws = torch.empty((G, B, K, nch, D, N), **f32)
+    dcw = torch.zeros((G, D, 4), **f32)
+    gr = (_cabi.Mamba1BwdGroup * G)()
+    dvc = dv.contiguous()
+    for g in range(G):
+        gr[g].dout = dvc[g].data_ptr()
+        gr[g].d_xz_scan, gr[g].du, gr[g].ddelta = d_xz_scan[g].data_ptr(), du[g].data_ptr(), ddelta[g].data_ptr()
+        gr[g].d_x_dbl, gr[g].dA = d_x_dbl[g].data_ptr(), dA[g].data_ptr()
+        gr[g].dD = dD[g].data_ptr() if D_h[g] is not None else None
+        gr[g].d_dt_bias = ddtb[g].data_ptr() if dtb_h[g] is not None else None
+        gr[g].state_workspace = ws[g].data_ptr()
+        gr[g].d_conv_weight = dcw[g].data_ptr()
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _cabi.check(_cabi.lib().dm_mamba1_scan_bwd(C.byref(a), gr, 1, st), "dm_mamba1_scan_bwd(phase 1, SSD operands)")
+    ops.LAUNCH_COUNTER["kernels"] += 1
+    if any(d is None for d in dtb_h):       # the kernel skipped the accumulation: d(dt_bias) is sum of d(delta_raw)
+        ddtb = ddelta.sum(dim=(1, 2, 3))
+    return dict(dz=d_xz_scan[..., D:], du=du, ddelta=ddelta, dB=d_x_dbl[..., R:R + N], dC=d_x_dbl[..., R + N:],
+                dA=dA, dD=dD, ddtb=ddtb)
+
+
+def mamba2_backward(zx, weights, plan, d_inner, d_state, nheads, v, gv, gss, s6_backward=s6_backward_cuda):
+    """Gradients of ``ops.mamba2_ssd_raw`` w.r.t. zxbcdt and (conv_weight, conv_bias, dt_bias, A, D) of every group.
+
+    Device-agnostic glue (split, conv recomputation and its backward on torch ops, per-head reductions, scatter back
+    to source tokens) around ``s6_backward`` -- the CUDA reverse scan in the product; tests substitute the oracle's
+    autograd to check the glue on CPU.  gv: gradient of v (plan.out_shape); gss: gradient of sumsq (G,B,K,rows) or None.
+    """
+    if plan.layout == "disjoint":
+        raise NotImplementedError("diffma_b200: Mamba-2 backward for the EfficientVMamba split (broken in the reference "
+                                  "itself, block/mamba2.py:704)")
+    G = len(zx)
+    D, N, H = d_inner, d_state, nheads
+    P = D // H
+    Cc = D + 2 * N
+    act = zx[0].dtype
+    # total gradient of v: direct + through sumsq = sum_c v^2 (the RMSNorm statistic the forward hands out)
+    dv = gv.float()
+    if gss is not None:
+        g2 = gss.float()
+        g2 = g2.transpose(2, 3).unsqueeze(-1) if plan.layout == "concat" else g2.unsqueeze(-1)   # -> v's row layout
+        dv = dv + 2.0 * v.float() * g2
+    dv = dv.to(act)
+    # recompute the conv + SiLU in scan order with torch ops (fp32), keeping the graph for its backward
+    xbc_scan, acts, u, Bm, Cm, dt_raw, cw, cb = [], [], [], [], [], [], [], []
+    with torch.enable_grad():
+        for g in range(G):
+            w = weights[g]
+            xs = gather_scan_order(zx[g][..., D:D + Cc], plan).float().requires_grad_(True)     # (B,K,L,Cc)
+            wg = w.conv_weight.detach().float().requires_grad_(True)
+            bg = None if w.conv_bias is None else w.conv_bias.detach().float().requires_grad_(True)
+            B_, K, L, _ = xs.shape
+            pre = torch.nn.functional.conv1d(xs.reshape(B_ * K, L, Cc).transpose(1, 2), wg.unsqueeze(1), bg,
+                                             padding=wg.shape[1] - 1, groups=Cc)[..., :L]
+            a = torch.nn.functional.silu(pre).transpose(1, 2).reshape(B_, K, L, Cc)
+            xbc_scan.append(xs); acts.append(a); cw.append(wg); cb.append(bg)
+            u.append(a[..., :D].detach().to(act))
+            Bm.append(a[..., D:D + N].detach())
+            Cm.append(a[..., D + N:].detach())
+            dt_raw.append(gather_scan_order(zx[g][..., D + Cc:], plan).float())
+    r = s6_backward(torch.stack(u), [zx[g][..., :D] for g in range(G)], torch.stack(dt_raw), torch.stack(Bm),
+                    torch.stack(Cm), [w.A for w in weights], [w.D for w in weights], [w.dt_bias for w in weights],
+                    dv, plan, H)
+    dzx, grads = [], []
+    for g in range(G):
+        w = weights[g]
+        d_act = torch.cat([r["du"][g], r["dB"][g], r["dC"][g]], dim=-1)
+        wanted = [xbc_scan[g], cw[g]] + ([cb[g]] if cb[g] is not None else [])
+        got = torch.autograd.grad(acts[g], wanted, grad_outputs=d_act)
+        B_, K, L, _ = d_act.shape
+        ddt = r["ddelta"][g].reshape(B_, K, L, H, P).sum(-1)
+        d_scan = torch.cat([r["dz"][g], got[0], ddt], dim=-1)                                   # (B,K,L,2D+2N+H)
+        dzx.append(scan_to_token_sum(d_scan, plan).to(act))
+        per = {"conv_weight": got[1], "conv_bias": got[2] if cb[g] is not None else None,
+               "dt_bias": None if w.dt_bias is None else r["ddtb"][g].reshape(H, P).sum(-1),
+               "A": r["dA"][g].reshape(H, P * N).sum(-1),
+               "D": None if w.D is None else r["dD"][g].reshape(H, P).sum(-1)}
+        grads += [per[f] for f in _W2]
+    return dzx, grads
+
+
 class Mamba2SsdFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, G, d_inner, d_state, nheads, gate, want_sumsq, *tensors):
@@ -141,12 +287,28 @@ class Mamba2SsdFn(torch.autograd.Function):
         n = len(_W2)
         weights = [ops.Mamba2Weights(*[_det(v) for v in flat[g * n:(g + 1) * n]]) for g in range(G)]
         v, ss = ops.mamba2_ssd_raw(zx, weights, plan, d_inner, d_state, nheads, gate, want_sumsq)
+        ctx.plan, ctx.G, ctx.dims, ctx.gate, ctx.want_sumsq = plan, G, (d_inner, d_state, nheads), gate, want_sumsq
+        ctx.none_mask = [t is None for t in flat]
+        ctx.save_for_backward(*zx, *[t for t in flat if t is not None], v)
         if ss is None:
             ss = v.new_zeros(())
-        ctx.mark_non_differentiable(ss)
+            ctx.mark_non_differentiable(ss)
         return v, ss
 
     @staticmethod
     def backward(ctx, gv, gss):
-        raise NotImplementedError("diffma_b200: the Mamba-2 backward kernel is not built yet; training with "
-                                  "--use-mamba2 is a later milestone (DESIGN.md)")
+        if not ctx.gate:
+            raise NotImplementedError("diffma_b200: Mamba-2 backward is built for the gated output (gate=True), the "
+                                      "only form DiffMa uses")
+        plan, G = ctx.plan, ctx.G
+        saved = list(ctx.saved_tensors)
+        v = saved.pop()
+        zx = saved[:G]
+        it = iter(saved[G:])
+        flat = [None if m else next(it) for m in ctx.none_mask]
+        n = len(_W2)
+        weights = [ops.Mamba2Weights(*flat[g * n:(g + 1) * n]) for g in range(G)]
+        d_inner, d_state, nheads = ctx.dims
+        dzx, grads = mamba2_backward(zx, weights, plan, d_inner, d_state, nheads, v, gv,
+                                     gss if ctx.want_sumsq else None)
+        return (None, None, None, None, None, None, None, *dzx, *grads)

@@ -1,11 +1,13 @@
 """CPU restatement of the external ops DiffMa's mixers call (TEST INFRASTRUCTURE).
 
-PARITY UNPINNED: the originals live in the un-vendored wheels ``mamba-ssm==2.0.4`` and
+PARITY UNPINNED against the reference's own wheels (second-source pin below): the originals live in the un-vendored wheels ``mamba-ssm==2.0.4`` and
 ``causal-conv1d==1.2.2.post1`` (reference ``environment.yml:67,36``), imported by the
 reference at ``block/mamba.py:11-23`` and ``block/mamba2.py:9-21``.  Each function
 below restates the *published reference algorithm* of the named upstream function
  in plain torch on CPU; the reference call sites that fix the
-argument meaning are cited per function.
+argument meaning are cited per function.  Second source: ``tests/test_oracle_vllm_pin.py`` checks these
+functions against outputs of vLLM 0.22's ports of the same upstream kernels recorded on a B200
+(``tests/golden/vllm_*.npz``, generator ``tests/golden/make_golden_vllm.py``).
 
 All functions compute in ``compute_dtype`` (fp32 by default, fp64 for tight checks)
 and return tensors in the input dtype, like the upstream ``*_ref`` functions do.

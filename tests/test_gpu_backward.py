@@ -112,3 +112,98 @@ def test_training_step_bf16_autocast_runs_and_matches_fp32_direction(dev):
               "blocks.3.mamba1.A_log", "blocks.1.mamba2.conv1d.weight"):
         cos = torch.nn.functional.cosine_similarity(grads["fp32"][n], grads["bf16"][n], dim=0).item()
         assert cos > 0.98, (n, cos)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Mamba-2 (training): autograd through dm_mamba2_ssd_fwd + the reverse-scan kernel fed with
+# SSD operands (autograd_ops.Mamba2SsdFn) vs autograd of the oracle
+# ---------------------------------------------------------------------------------------------------------
+def _m2_params(d_model, seed, d_in=1024, N=16, H=16):
+    g = torch.Generator().manual_seed(seed)
+    cc = d_in + 2 * N
+    return dict(conv_w=torch.randn(cc, 4, generator=g) * 0.4, conv_b=torch.randn(cc, generator=g) * 0.1,
+                dt_bias=torch.randn(H, generator=g) * 0.5 - 1.5, A=-torch.exp(0.5 * torch.randn(H, generator=g)),
+                D=1 + 0.1 * torch.randn(H, generator=g), norm_w=1 + 0.1 * torch.randn(d_in, generator=g),
+                out_proj=torch.randn(d_model, d_in, generator=g) / d_in ** 0.5)
+
+
+@pytest.mark.parametrize("B,L", [(2, 21), (1, 70)])
+def test_mamba_split_conv1d_scan_combined_grads_fp32(dev, B, L):
+    from diffma_b200 import ops
+    from oracle import ref_ops
+    torch.set_grad_enabled(True)
+    d_in, N, H, dm = 1024, 16, 16, 64
+    g = torch.Generator().manual_seed(L)
+    zx = torch.randn(B, L, 2 * d_in + 2 * N + H, generator=g)
+    p = _m2_params(dm, seed=L + 1)
+    gout = torch.randn(B, L, dm, generator=g)
+    order = ["conv_w", "conv_b", "dt_bias", "A", "D", "norm_w", "out_proj"]
+
+    def run(fn, to):
+        leaves = {k: to(v).clone().requires_grad_(True) for k, v in p.items()}
+        x = to(zx).clone().requires_grad_(True)
+        out = fn(x, leaves["conv_w"], leaves["conv_b"], leaves["dt_bias"], leaves["A"], leaves["D"], 256,
+                 rmsnorm_weight=leaves["norm_w"], rmsnorm_eps=1e-5, outproj_weight=leaves["out_proj"], headdim=64,
+                 ngroups=1, norm_before_gate=False)
+        out.backward(to(gout))
+        return out.detach().cpu(), x.grad.cpu(), [leaves[k].grad.cpu() for k in order]
+
+    o_ref, gx_ref, gw_ref = run(ref_ops.mamba_split_conv1d_scan_ref, lambda t: t)
+    o, gx, gw = run(ops.mamba_split_conv1d_scan_combined, lambda t: t.to(dev))
+    torch.set_grad_enabled(False)
+    assert _relerr(o, o_ref) < 1e-3
+    assert _relerr(gx, gx_ref) < 3e-3, ("zxbcdt", _relerr(gx, gx_ref))
+    for name, a, b in zip(order, gw, gw_ref):
+        assert _relerr(a, b) < 3e-3, (name, _relerr(a, b))
+
+
+def test_spiral_mamba2_mixer_grads_match_oracle(dev):
+    from diffma_b200 import mixer, scan_orders, synth
+    from oracle import ref_model
+    torch.set_grad_enabled(True)
+    ml, inv = scan_orders.spiral(4)
+    kw = dict(token_list=ml[2], token_list_reversal=ml[3], origina_list=inv[2], origina_list_reversal=inv[3])
+    torch.manual_seed(0)
+    m = mixer.Mamba2(d_model=512, d_state=16, d_conv=4, expand=2, **kw)
+    synth.fill_trained_like_(m, seed=5)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    h = torch.randn(2, 16, 512, generator=g)
+    gout = torch.randn(2, 16, 512, generator=g)
+    h_ref = h.clone().requires_grad_(True)
+    ref_model.mamba2_mixer_ref(sd, "", h_ref, "spiral", kw).backward(gout)
+    m = m.to(dev)
+    h_gpu = h.to(dev).requires_grad_(True)
+    m(h_gpu, "spiral").backward(gout.to(dev))
+    torch.set_grad_enabled(False)
+    assert _relerr(h_gpu.grad.cpu(), h_ref.grad) < 3e-3
+    for name, prm in m.named_parameters():
+        assert prm.grad is not None, name
+        assert _relerr(prm.grad.cpu(), sd[name].grad) < 4e-3, (name, _relerr(prm.grad.cpu(), sd[name].grad))
+
+
+def test_mamba2_training_step_bf16_runs(dev):
+    """DiffMa-S/4 --use-mamba2: training_losses + backward under bf16 autocast gives finite gradients for every
+    parameter and points the same way as the fp32 run."""
+    from diffma_b200 import create_model_and_diffusion, synth
+    torch.set_grad_enabled(True)
+    grads = {}
+    for mode in ("fp32", "bf16"):
+        torch.manual_seed(0)
+        net, diffusion = create_model_and_diffusion("DiffMa-S/4", use_mamba2=True, respacing="")
+        synth.fill_trained_like_(net, seed=11)
+        net = net.to(dev).train()
+        b = synth.synthetic_batch(4, tokens=49, seed=9, device=dev)
+        t = torch.tensor([10, 200, 500, 900], device=dev)
+        noise = torch.randn(4, 4, 28, 28, generator=torch.Generator().manual_seed(1)).to(dev)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+            loss = diffusion.training_losses(net, b["x"], t, dict(y=b["y"], y2=b["y2"], w=b["w"]), noise=noise)["loss"].mean()
+        loss.backward()
+        assert torch.isfinite(loss)
+        grads[mode] = {n: p.grad.detach().float().flatten() for n, p in net.named_parameters() if p.grad is not None}
+        assert all(torch.isfinite(v).all() for v in grads[mode].values())
+    torch.set_grad_enabled(False)
+    for n in ("blocks.1.mamba1.in_proj.weight", "blocks.2.mamba2.out_proj.weight", "blocks.3.mamba1.A_log",
+              "blocks.1.mamba2.conv1d.weight", "blocks.0.mamba1.dt_bias", "blocks.2.mamba1.norm.weight"):
+        cos = torch.nn.functional.cosine_similarity(grads["fp32"][n], grads["bf16"][n], dim=0).item()
+        assert cos > 0.97, (n, cos)
