@@ -68,6 +68,11 @@ def forward_ref(zx, w, plan):
 
 @pytest.mark.parametrize("layout,K", [("concat", 3), ("stacked", 2), ("concat", 1)])
 def test_mamba2_backward_glue_matches_autograd(layout, K):
+    with torch.enable_grad():       # other test modules switch autograd off globally at import
+        _run_glue_case(layout, K)
+
+
+def _run_glue_case(layout, K):
     torch.manual_seed(3)
     B, L, G = 2, 9, 2
     orders = [None] + [torch.randperm(L).tolist() for _ in range(K - 1)] if K > 1 else [torch.randperm(L).tolist()]
