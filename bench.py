@@ -134,6 +134,40 @@ def build_model(args, device):
     return net.to(device).eval(), diffusion
 
 
+def upstream_cuda_scan_us(n_seq, D, L, device, flush, iters=10):
+    """The upstream selective-scan CUDA kernel at the same shape, as a comparator (never on our path): vLLM's
+    ``torch.ops._C.selective_scan_fwd`` is a port of mamba_ssm's ``selective_scan_fwd_kernel.cuh`` (the reference's
+    wheel itself has no sm_100 build and is not installable offline).  It covers ONLY the scan + gate: dt_proj,
+    conv1d and x_proj are separate launches upstream, while our scan kernel includes dt_proj.  None if unavailable."""
+    try:
+        from vllm.model_executor.layers.mamba.ops.mamba_ssm import selective_scan_fn
+        bf = torch.bfloat16
+        u = torch.randn(n_seq, D, L, device=device, dtype=bf)
+        delta = (torch.randn(n_seq, D, L, device=device) * 0.5).to(bf)
+        z = torch.randn(n_seq, D, L, device=device, dtype=bf)
+        Bm = torch.randn(n_seq, 1, 16, L, device=device, dtype=bf)
+        Cm = torch.randn(n_seq, 1, 16, L, device=device, dtype=bf)
+        A = -torch.arange(1, 17, device=device).float().repeat(D, 1)
+        Dv, dtb = torch.ones(D, device=device), torch.full((D,), -4.0, device=device)
+        states = torch.zeros(n_seq, D, 16, device=device, dtype=bf)
+        ts = []
+        for i in range(iters + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            selective_scan_fn(u, states, delta, A, Bm, Cm, Dv, z=z, delta_bias=dtb, delta_softplus=True)
+            e1.record()
+            torch.cuda.synchronize(device)
+            if i >= 2:
+                ts.append(e0.elapsed_time(e1) * 1e3)
+        ts.sort()
+        return {"launch_us": round(ts[len(ts) // 2], 1), "shape": [n_seq, D, L],
+                "impl": "vLLM torch.ops._C.selective_scan_fwd (port of mamba_ssm selective_scan_fwd_kernel.cuh), bf16, "
+                        "scan + gate only"}
+    except Exception as e:      # noqa: BLE001 -- comparator only
+        return {"unavailable": repr(e)[:200]}
+
+
 def kernel_roofline(args, device, peaks):
     """Time the dominant kernel alone at the workload's per-block shape (2 mixers x 3 directions x batch)."""
     from diffma_b200 import _cabi, ops, scan_orders
@@ -169,6 +203,7 @@ def kernel_roofline(args, device, peaks):
                 ev[i][1].record()
             torch.cuda.synchronize(device)
             res[name] = sorted(e0.elapsed_time(e1) for e0, e1 in ev)[iters // 2] * 1e-3
+        upstream = upstream_cuda_scan_us(2 * B * 3, D, L, device, flush)
         token_scans = 2 * B * 3 * L
         # algorithmic bytes of the scan kernel per token-scan: read u, z (2*D*2 B) + x_dbl (64*4 B),
         # write y*silu(z) (D*2 B)
@@ -176,6 +211,7 @@ def kernel_roofline(args, device, peaks):
         dom, t = "m1_scan_kernel", res["m1_scan_kernel"]
         exps = token_scans * D * 19           # 16 decays + softplus (2) + silu(z) (1, tanh) MUFU ops per (token, channel)
     else:
+        upstream = None
         Cin = 2 * D + 32 + 16
         zx = [torch.randn(B, L, Cin, generator=g).to(device, torch.bfloat16) for _ in range(2)]
         w = [ops.Mamba2Weights((torch.randn(D + 32, 4, generator=g) * 0.4).to(device), torch.zeros(D + 32, device=device),
@@ -210,7 +246,7 @@ def kernel_roofline(args, device, peaks):
             "peak_source": "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback B200_PROFILING.md",
             "launch_us": {k: round(v * 1e6, 2) for k, v in res.items()},
             "token_scans_per_launch": token_scans, "algorithmic_bytes_per_token_scan": bytes_per,
-            "binding_pipe": "mufu" if not args.mamba2 else "fp32",
+            "binding_pipe": "mufu" if not args.mamba2 else "fp32", "upstream_cuda_scan": upstream,
             "mufu": {"achieved_gexp_s": round(exps / t / 1e9, 1), "peak_gexp_s": round(mufu_peak / 1e9, 1),
                      "frac": round(exps / t / mufu_peak, 4),
                      "note": "148 SM x 16 MUFU/clk x sm_max_mhz; the scan is instruction-bound on this pipe (DESIGN.md)"}}

@@ -9,13 +9,13 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-DM_ABI_VERSION = 2
+DM_ABI_VERSION = 3
 DM_OK, DM_ERR_INVALID_ARG, DM_ERR_UNSUPPORTED, DM_ERR_CUDA = 0, -1, -2, -4
 DM_F32, DM_BF16 = 0, 1
 DM_MAX_GROUPS = 4
 DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
-EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_scan_bwd", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
+EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
            "dm_spiral_post_mix", "dm_gemm_bf16_tn", "dm_p_sample_update", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
@@ -38,6 +38,7 @@ class Mamba1Args(C.Structure):
         ("act_dtype", C.c_int32), ("out_order", C.c_int32), ("n_groups", C.c_int32),
         ("order", C.c_void_p),
         ("group", Mamba1Group * DM_MAX_GROUPS),
+        ("sched_workspace", C.c_void_p), ("sched_workspace_bytes", C.c_int64),
     ]
 
 
@@ -92,6 +93,8 @@ def lib() -> C.CDLL:
     L.dm_build_info.restype = C.c_char_p
     L.dm_mamba1_scan_fwd.restype = C.c_int
     L.dm_mamba1_scan_fwd.argtypes = [C.POINTER(Mamba1Args), C.c_void_p]
+    L.dm_mamba1_sched_workspace_bytes.restype = C.c_int64
+    L.dm_mamba1_sched_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     L.dm_mamba1_scan_phase.restype = C.c_int
     L.dm_mamba1_scan_phase.argtypes = [C.POINTER(Mamba1Args), C.c_int, C.c_void_p]
     L.dm_mamba1_scan_bwd.restype = C.c_int

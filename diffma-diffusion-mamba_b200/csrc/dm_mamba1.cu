@@ -55,6 +55,9 @@ struct M1P {
     int out_order, n_groups;
     int tiles_per_seq;
     const int32_t* order;
+    // dynamic schedule of the scan kernel (see m1_scan_kernel): workspace + segmentation, or sched == nullptr
+    int* sched;
+    int seg_chunks, n_segs;
     M1G g[DM_MAX_GROUPS];
 };
 
@@ -577,18 +580,85 @@ __device__ __forceinline__ void ldmatrix_x4_u(uint32_t (&r)[4], uint32_t addr) {
                  : "r"(addr));
 }
 
-template <typename T, int CPL>
+#ifdef DM_SCAN_TRACE
+// debugging aid (tools/scan_trace.py): per warp-unit {smid, warpid, start clock, end clock}
+__device__ unsigned long long g_scan_trace[4 * 8192];
+#endif
+
+// Scheduling.  kDyn = false: one CTA (= one warp) per warp-unit, the whole sequence (small problems, fp32).
+// kDyn = true: PERSISTENT warps (grid = resident warp slots) consume a READY QUEUE in the caller's workspace.  A work
+// item is one SEGMENT (seg_chunks chunks of 8 tokens) of one warp-unit.  Consumer tickets (atomic head) below n_units
+// are the first segments, ready from the start; ticket n_units + j is whatever the j-th hand-over pushes: a warp that
+// finishes a segment stores the recurrence state (32 lanes x 2 channels x 16 states, 4 KB), fences, takes a producer
+// slot (atomic tail) and publishes (unit, next segment) there; the consumer polling that slot picks the unit up at
+// once.  Items therefore start only when their input state exists (nothing ever waits inside an item), successors go
+// to warps in COMPLETION order (no head-of-line blocking behind slow units), and the count of pushes provably covers
+// every ticket below n_items, so no consumer waits forever whatever the grid size.
+// Why: a static one-unit-per-warp launch leaves the sub-partitions of an SM with 2 or 3 warps (1536 units over 592
+// SMSPs): warps of a 3-warp SMSP live 114..137 us while 2-warp SMSPs are idle after 91 us (tools/scan_trace.py), and
+// a second wave (3072 units) is scheduled just as unevenly.
+// Workspace (ints): [0] head, [1] tail, [2] warps done, [16 + j] queue slot j (0 = empty, else 1 + seg * n_units +
+// unit), capacity kSchedMaxSegs * n_units; states at byte offset sched_state_offset(n_units), 4 KB per unit as
+// [16 pairs][32 lanes] x 8 B.  Consumers clear the slot they took and the last warp out clears the counters, so the
+// workspace is zeroed once at allocation and is re-armed after every launch (CUDA-graph replay included).
+constexpr int kSchedMaxSegs = 64;
+__host__ __device__ inline size_t sched_state_offset(int n_units) {
+    return (static_cast<size_t>(64) + static_cast<size_t>(4) * kSchedMaxSegs * n_units + 255) / 256 * 256;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename T, int CPL, bool kDyn>
 __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
+#ifdef DM_SCAN_TRACE
+    unsigned trace_sm, trace_warp;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(trace_sm));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(trace_warp));
+    unsigned long long trace_t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
+#endif
     constexpr bool kSplit = sizeof(T) == 4;
     constexpr int kSC = 32 * CPL;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x;
-    const int unit = blockIdx.x;
-    if (unit >= n_units) return;
     ScanSmem<T, CPL>& S = *reinterpret_cast<ScanSmem<T, CPL>*>(smem_raw);
-
     const int D = p.D, L = p.L;
     const int slices = D / kSC;
+    const int n_chunks = (L + kCH - 1) / kCH;
+    const bool token_order = p.out_order == DM_OUT_TOKEN_ORDER;
+    int* const sched = p.sched;
+    const int n_items = kDyn ? n_units * p.n_segs : n_units;
+    // consumer ticket -> work item (dynamic), or the CTA's own unit (static)
+    auto next_item = [&]() -> int {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(sched, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_items) return n_items;
+        if (t < n_units) return t;                               // first segments: ready from the start
+        int* slot = sched + 16 + (t - n_units);
+        int v;
+        while ((v = ld_acquire_gpu(slot)) == 0) __nanosleep(32);
+        __syncwarp();                                            // every lane has seen the entry
+        if (lane == 0) st_relaxed_gpu(slot, 0);                  // the slot is ours alone: leave it empty for the next launch
+        return v - 1;
+    };
+    int item = blockIdx.x;
+    if constexpr (kDyn) item = next_item();
+  while (item < n_items) {
+    int unit = item, seg = 0;
+    if constexpr (kDyn) {
+        seg = item / n_units;
+        unit = item - seg * n_units;
+    }
+    const int c_begin = kDyn ? seg * p.seg_chunks : 0;
+    const int c_end = kDyn ? min(n_chunks, c_begin + p.seg_chunks) : n_chunks;
+
     const int cs = unit % slices, seq = unit / slices;
     const int k = seq % p.K, b = (seq / p.K) % p.B, g = seq / (p.K * p.B);
     const M1G& G = p.g[g];
@@ -600,11 +670,18 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
     const float* xd_seq = G.x_dbl + seq_in_group * L * kE;
     char* out_lane = reinterpret_cast<char*>(static_cast<T*>(G.out) + static_cast<int64_t>(b) * G.out_bs +
                                              static_cast<int64_t>(k) * G.out_ds + c0 + lane);
-    const bool token_order = p.out_order == DM_OUT_TOKEN_ORDER;
     const int out_ts32 = static_cast<int>(G.out_ts * sizeof(T));
 
     // ---- W_dt slice -> shared (bf16 hi [, lo]) ----
-    {
+    if constexpr (!kSplit) {
+        // 16-byte cp.async segments (all in flight at once; completion rides on the first chunk's commit group)
+        const char* Wdt = reinterpret_cast<const char*>(static_cast<const T*>(G.wdt) + static_cast<int64_t>(c0) * kR);
+#pragma unroll
+        for (int i = 0; i < kSC * kR * 2 / 16 / 32; ++i) {
+            const int sgm = lane + 32 * i, row = sgm >> 2, part = sgm & 3;       // 4 x 16 B per 32-element row
+            cp_async16(smem_u32(&S.wdt[0][row][part * 8]), Wdt + sgm * 16);
+        }
+    } else {
         const T* Wdt = static_cast<const T*>(G.wdt) + static_cast<int64_t>(c0) * kR;
         for (int i = lane; i < kSC * kR / 2; i += 32) {
             const int row = i / (kR / 2), col = (i % (kR / 2)) * 2;
@@ -640,7 +717,7 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
     //      the last valid row, so the tail chunk needs no predicates (the duplicates are never consumed). ----
     constexpr int kSegU = kSC * sizeof(T) / 16;       // 16-byte segments per (token, 64 channels) row: 8 / 16
     auto prefetch = [&](int ci) {
-        const int buf = ci & 1, j0 = ci * kCH;
+        const int buf = (ci - c_begin) & 1, j0 = ci * kCH;
         {
             const uint32_t xdst = smem_u32(&S.xd[buf][0][0]) + lane * 16;
             const int part = lane & 15;
@@ -669,6 +746,9 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
     for (int ch = 0; ch < CPL; ++ch)
 #pragma unroll
         for (int n = 0; n < kN / 2; ++n) h[ch][n] = 0ull;      // bit pattern of (0.f, 0.f)
+    uint64_t* const h_ws = kDyn ? reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(sched) + sched_state_offset(n_units)) +
+                                      static_cast<size_t>(unit) * (CPL * (kN / 2) * 32) + lane
+                                : nullptr;
 
     // one token of the recurrence for both channels of the lane
     auto token = [&](int buf, int jj, const float (&dtv)[CPL]) {
@@ -720,12 +800,19 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
         }
     };
 
-    const int n_chunks = (L + kCH - 1) / kCH;
-    prefetch(0);
+    prefetch(c_begin);
+    if constexpr (kDyn) {
+        if (seg > 0) {                               // state left by the item that ran the previous segment of this unit
+#pragma unroll
+            for (int ch = 0; ch < CPL; ++ch)
+#pragma unroll
+                for (int n = 0; n < kN / 2; ++n) h[ch][n] = __ldcg(reinterpret_cast<const unsigned long long*>(h_ws) + (ch * (kN / 2) + n) * 32);
+        }
+    }
     __syncwarp();                                    // W_dt slice visible to every lane
-    for (int ci = 0; ci < n_chunks; ++ci) {
-        const int buf = ci & 1, j0 = ci * kCH;
-        if (ci + 1 < n_chunks) {
+    for (int ci = c_begin; ci < c_end; ++ci) {
+        const int buf = (ci - c_begin) & 1, j0 = ci * kCH;
+        if (ci + 1 < c_end) {
             prefetch(ci + 1);
             cp_async_wait<1>();
         } else {
@@ -801,10 +888,46 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
         }
         __syncwarp();
     }
+    if constexpr (kDyn) {
+        if (seg + 1 < p.n_segs) {                    // hand the state to whoever holds the next segment
+#pragma unroll
+            for (int ch = 0; ch < CPL; ++ch)
+#pragma unroll
+                for (int n = 0; n < kN / 2; ++n)
+                    __stcg(reinterpret_cast<unsigned long long*>(h_ws) + (ch * (kN / 2) + n) * 32, h[ch][n]);
+            __syncwarp();                            // every lane's state stores happen-before lane 0's fence
+            if (lane == 0) {
+                __threadfence();
+                const int slot = atomicAdd(sched + 1, 1);
+                st_relaxed_gpu(sched + 16 + slot, 1 + (seg + 1) * n_units + unit);
+            }
+        }
+    }
+#ifdef DM_SCAN_TRACE
+    if (lane == 0 && item < 8192) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        g_scan_trace[4 * item] = trace_sm; g_scan_trace[4 * item + 1] = trace_warp;
+        g_scan_trace[4 * item + 2] = trace_t0; g_scan_trace[4 * item + 3] = t1;
+        trace_t0 = t1;
+    }
+#endif
+    if constexpr (!kDyn) break;
+    // next ticket only now (no look-ahead: a ticket must be held by a warp that is free to poll)
+    item = next_item();
+  }
+    if constexpr (kDyn) {
+        // every warp checks out; the last one clears the counters (queue slots were cleared by their consumers)
+        if (lane == 0 && atomicAdd(sched + 2, 1) == static_cast<int>(gridDim.x) - 1) {
+            sched[0] = 0;
+            sched[1] = 0;
+            sched[2] = 0;
+        }
+    }
 }
 
 template <typename T>
-int launch_m1(const M1P& p, int phases, cudaStream_t stream) {
+int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes) {
     const int n_seq = p.n_groups * p.B * p.K;
     const bool split = sizeof(T) == 4;
     // kernel P
@@ -844,26 +967,56 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream) {
             int dev = 0;
             DM_CUDA_TRY(cudaGetDevice(&dev));
             DM_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(ScanSmem<T, 2>))));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(ScanSmem<T, 2>))));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(ScanSmem<T, 1>))));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
         // two channels per lane (fewer shared-memory reads per MUFU op, 168 registers) when that still leaves >= 8
         // warps per SM; otherwise one channel per lane doubles the number of warp-units (small batches, config C5)
         const int units2 = n_seq * (p.D / 64);
-        static int force_cpl = -1;
+        static int force_cpl = -1, force_sched = -1, force_seg = 0;
         if (force_cpl < 0) {
             const char* e = getenv("DM_SCAN_CPL");
             force_cpl = e ? atoi(e) : 0;
+            e = getenv("DM_SCAN_SCHED");                 // "static" | "dynamic" (default: dynamic when a workspace is given)
+            force_sched = e ? (e[0] == 's' ? 0 : 1) : 2;
+            e = getenv("DM_SCAN_SEG");                   // chunks (of 8 tokens) per work item of the dynamic schedule
+            force_seg = e ? atoi(e) : 0;
         }
         if (force_cpl == 2 || (force_cpl == 0 && units2 >= 8 * n_sm)) {
-            m1_scan_kernel<T, 2><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
+            const int n_chunks = (p.L + kCH - 1) / kCH;
+            const int slots = 12 * n_sm;                                      // resident warps (168 registers)
+            const bool have_ws = p.sched != nullptr && sched_bytes >= sched_state_offset(units2) + static_cast<size_t>(units2) * 4096;
+            // Measured on B200 (profiles/r01_notes.md): with at most one warp-unit per resident slot every chain is in
+            // flight from the start and a hand-over only adds ~3.5 us to it (static wins: 140 vs 147 us at 1536 units);
+            // with more units than slots the queue keeps all 12 warps of every SM busy until the end (-4 .. -13 %).
+            const bool dyn = force_sched == 1 || (force_sched == 2 && units2 > slots);
+            if (have_ws && dyn && n_chunks >= 8) {
+                M1P q = p;
+                // ~5 work items per resident warp bounds the idle tail at the end; fewer, longer items = fewer hand-overs
+                int segs = force_seg > 0 ? (n_chunks + force_seg - 1) / force_seg
+                                         : static_cast<int>((5ll * slots + units2 - 1) / units2);
+                if (segs < 2 && force_seg <= 0) segs = 2;
+                if (segs > n_chunks / 4) segs = n_chunks / 4;
+                if (segs < 1) segs = 1;
+                if (segs > kSchedMaxSegs) segs = kSchedMaxSegs;
+                q.seg_chunks = (n_chunks + segs - 1) / segs;
+                q.n_segs = (n_chunks + q.seg_chunks - 1) / q.seg_chunks;
+                const long long items = static_cast<long long>(units2) * q.n_segs;
+                const int grid = items < slots ? static_cast<int>(items) : slots;
+                m1_scan_kernel<T, 2, true><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
+            } else {
+                m1_scan_kernel<T, 2, false><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
+            }
         } else {
             const int units1 = n_seq * (p.D / 32);
-            m1_scan_kernel<T, 1><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
+            m1_scan_kernel<T, 1, false><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
         }
         DM_CUDA_TRY(cudaGetLastError());
     }
@@ -904,11 +1057,28 @@ static int m1_dispatch(const dm_mamba1_args* a, int phases, void* stream) {
         d.conv_w = s.conv_weight; d.conv_b = s.conv_bias; d.wx = s.x_proj_weight; d.wdt = s.dt_proj_weight;
         d.dt_bias = s.dt_bias; d.A = s.A; d.D = s.D;
     }
+    if (a->sched_workspace != nullptr && !aligned16(a->sched_workspace)) return DM_ERR_INVALID_ARG;
+    p.sched = static_cast<int*>(a->sched_workspace);
+    const size_t sched_bytes = a->sched_workspace ? static_cast<size_t>(a->sched_workspace_bytes) : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return a->act_dtype == DM_F32 ? launch_m1<float>(p, phases, st) : launch_m1<__nv_bfloat16>(p, phases, st);
+    return a->act_dtype == DM_F32 ? launch_m1<float>(p, phases, st, sched_bytes)
+                                  : launch_m1<__nv_bfloat16>(p, phases, st, sched_bytes);
 }
 
 extern "C" int dm_mamba1_scan_fwd(const dm_mamba1_args* a, void* stream) { return m1_dispatch(a, 3, stream); }
+
+extern "C" int64_t dm_mamba1_sched_workspace_bytes(int32_t batch, int32_t n_dir, int32_t d_inner, int32_t n_groups) {
+    if (batch <= 0 || n_dir <= 0 || d_inner <= 0 || n_groups <= 0) return 0;
+    const long long units = static_cast<long long>(n_groups) * batch * n_dir * (d_inner / 64);
+    if (units > (1ll << 24)) return 0;
+    return static_cast<int64_t>(dm::sched_state_offset(static_cast<int>(units)) + static_cast<size_t>(units) * 4096);
+}
+
+#ifdef DM_SCAN_TRACE
+extern "C" int dm_debug_scan_trace(unsigned long long* host_out, int n_units) {
+    return cudaMemcpyFromSymbol(host_out, dm::g_scan_trace, sizeof(unsigned long long) * 4 * n_units) == cudaSuccess ? 0 : -4;
+}
+#endif
 
 extern "C" int dm_mamba1_scan_phase(const dm_mamba1_args* a, int phase, void* stream) {
     if (phase != 1 && phase != 2) return DM_ERR_INVALID_ARG;

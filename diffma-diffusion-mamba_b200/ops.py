@@ -171,7 +171,25 @@ def _strides(x: torch.Tensor):
     return bs, ts
 
 
-def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, bufs=None):
+# scratch of the scan kernel's dynamic schedule: one zero-initialised buffer per (device, launch geometry), kept alive
+# for the life of the process (CUDA graphs hold its address); every launch leaves it re-armed (include/diffma_b200.h)
+_SCHED_WS = {}
+USE_DYNAMIC_SCHEDULE = True
+
+
+def _sched_workspace(device, batch: int, n_dir: int, d_inner: int, groups: int):
+    key = (str(device), batch, n_dir, d_inner, groups)
+    ws = _SCHED_WS.get(key)
+    if ws is None:
+        need = int(_cabi.lib().dm_mamba1_sched_workspace_bytes(batch, n_dir, d_inner, groups))
+        if need <= 0:
+            return None
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        _SCHED_WS[key] = ws
+    return ws
+
+
+def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, bufs=None, dynamic=None):
     """Fill a ``dm_mamba1_args`` for the given groups.  Returns (args, (out, u, x_dbl)); the tensors own the memory
     the struct points at and must outlive the launch.  ``bufs`` = existing (out-shaped, u, x_dbl) tensors to point at
     instead of allocating (the backward passes dout / the saved intermediates)."""
@@ -190,6 +208,10 @@ def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: Scan
     a.d_inner, a.d_state, a.dt_rank, a.d_conv = D, N, R, weights[0].conv_weight.shape[1]
     a.act_dtype, a.out_order, a.n_groups = _dtype_code(x0), plan.out_order, G
     a.order = _ptr(plan.table)
+    if USE_DYNAMIC_SCHEDULE if dynamic is None else dynamic:
+        ws = _sched_workspace(x0.device, B, plan.n_dir, D, G)
+        if ws is not None:
+            a.sched_workspace, a.sched_workspace_bytes = ws.data_ptr(), ws.numel()
     obs, ods, ots = plan.out_strides(D)
     # one allocation per kind so groups are adjacent (lets callers view them as a batch)
     if bufs is None:

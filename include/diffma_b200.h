@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 2
+#define DM_ABI_VERSION 3
 
 typedef enum {
     DM_OK = 0,
@@ -96,9 +96,19 @@ typedef struct {
                                   source token order[k*seqlen+j]; NULL = every direction is the identity.
                                   A first entry order[k*seqlen] == -1 marks direction k as the identity.   */
     dm_mamba1_group group[DM_MAX_GROUPS];
+    /* Optional scratch of the scan kernel's dynamic schedule (persistent warps consuming a ready queue of ~40-token
+     * segments; the recurrence state crosses segments through this buffer).  NULL = static schedule, one warp per
+     * (sequence, 64 channels).  At least dm_mamba1_sched_workspace_bytes(...) bytes, 16-byte aligned, ZEROED ONCE by
+     * the caller when allocated: every launch leaves it re-armed.  One workspace must not be used by launches that
+     * can run concurrently (different streams). */
+    void* sched_workspace;
+    int64_t sched_workspace_bytes;
 } dm_mamba1_args;
 
 int dm_mamba1_scan_fwd(const dm_mamba1_args* args, void* stream);
+
+/* Size of `sched_workspace` for a launch of n_groups x batch x n_dir sequences of d_inner channels (0 = none). */
+int64_t dm_mamba1_sched_workspace_bytes(int32_t batch, int32_t n_dir, int32_t d_inner, int32_t n_groups);
 
 /* The two kernels of dm_mamba1_scan_fwd separately, for profiling and the backward's recomputation:
  * phase 1 = gather + conv1d + SiLU + x_proj (writes u, x_dbl); phase 2 = dt_proj + scan + gate (reads them). */

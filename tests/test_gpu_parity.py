@@ -315,3 +315,41 @@ def test_graphed_sampler_matches_eager_steps(dev, monkeypatch):
         s.step()
     torch.testing.assert_close(s.x, x, rtol=1e-4, atol=1e-4)
     assert s.kernels_per_step > 0          # the step really launches this package's kernels
+
+
+# ---------------------------------------------------------------------------------------------------------
+# dynamic (ticketed, segmented) schedule of the scan kernel: same arithmetic in the same order as the static
+# one-warp-per-unit launch => bit-identical outputs, launch after launch (the workspace re-arms itself)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,side", [(20, 14), (32, 10), (24, 9), (40, 14)])
+def test_dynamic_scan_schedule_is_bit_identical_to_static(B, side):
+    """More warp-units than resident warps (2*B*3*16 > 12*148), so the library picks the ready-queue schedule."""
+    import ctypes as C
+    from diffma_b200 import _cabi, ops, scan_orders
+    dev = torch.device("cuda:0")
+    L, D = side * side, 1024
+    ml, _ = scan_orders.spiral(side)
+    plan = ops.ScanPlan.build([None, ml[0], ml[1]], L, "concat", dev)
+    g = torch.Generator().manual_seed(B + side)
+    bf = torch.bfloat16
+    xz = [torch.randn(B, L, 2 * D, generator=g).to(dev, bf) for _ in range(2)]
+    w = [ops.Mamba1Weights((torch.randn(D, 4, generator=g) * 0.4).to(dev), (torch.randn(D, generator=g) * 0.1).to(dev),
+                           (torch.randn(64, D, generator=g) / 32).to(dev, bf), (torch.randn(D, 32, generator=g) / 5.6).to(dev, bf),
+                           (torch.randn(D, generator=g) - 3).to(dev),
+                           -torch.exp(torch.log(torch.arange(1, 17).float()).expand(D, 16)
+                                      + 0.3 * torch.randn(D, 16, generator=g)).contiguous().to(dev),
+                           torch.ones(D, device=dev)) for _ in range(2)]
+    lib, st = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    a_s, keep_s = ops.mamba1_args(xz, w, plan, dynamic=False)
+    assert not a_s.sched_workspace
+    _cabi.check(lib.dm_mamba1_scan_fwd(C.byref(a_s), st), "static")
+    a_d, keep_d = ops.mamba1_args(xz, w, plan, dynamic=True)
+    assert a_d.sched_workspace and a_d.sched_workspace_bytes >= 4096 * 2 * B * 3 * (D // 64)
+    for rep in range(3):
+        keep_d[0].zero_()
+        _cabi.check(lib.dm_mamba1_scan_fwd(C.byref(a_d), st), "dynamic")
+        torch.cuda.synchronize()
+        assert torch.equal(keep_d[0], keep_s[0]), f"launch {rep}: dynamic schedule differs from static"
+    ws = ops._sched_workspace(dev, B, 3, D, 2)
+    n_units = 2 * B * 3 * (D // 64)
+    assert int(ws[: 64 + 256 * n_units].view(torch.int32).abs().sum()) == 0, "workspace (counters + ready queue) not re-armed"
