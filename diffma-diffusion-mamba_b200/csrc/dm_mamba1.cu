@@ -526,15 +526,15 @@ __device__ __forceinline__ float lg2_approx(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// softplus with torch's threshold (identity above 20).  e = exp(x); for e >= 2^-7 log(1+e) through MUFU.LG2
-// (1+e rounds with relative error <= 6e-8/e <= 8e-6), below that the series e - e^2/2 + e^3/3 (error < 2e-7).
-__device__ __forceinline__ float softplus_fast(float x) {
-    const float e = ex2_approx(x * kLog2e);
-    const float big = lg2_approx(1.0f + e) * 0.6931471805599453f;
-    const float small = e * fmaf(e, fmaf(e, 0.33333333f, -0.5f), 1.0f);
-    const float r = e < 0.0078125f ? small : big;
-    return x > 20.0f ? x : r;
+// softplus with torch's threshold (identity above 20), argument already scaled: s = x * log2(e).
+// ln(1 + e^x) = ln2 * lg2(1 + 2^s): two MUFU + 3 FMA-pipe instructions.  1 + 2^s rounds with absolute error <= 6e-8,
+// i.e. dt carries an ABSOLUTE error <= 4e-8 -- immaterial next to dt's bf16 / tf32 inputs, and for dt that small the
+// state update dt*B*u and the decay 1 - dt*|A| are unaffected at fp32 resolution.
+__device__ __forceinline__ float softplus_scaled(float s) {
+    const float l = lg2_approx(1.0f + ex2_approx(s));
+    return 0.6931471805599453f * (s > 28.853900817779268f ? s : l);
 }
+__device__ __forceinline__ float softplus_fast(float x) { return softplus_scaled(x * kLog2e); }
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
             A2[ch][n / 2] = pack2(t.x * kLog2e, t.y * kLog2e);
             A2[ch][n / 2 + 1] = pack2(t.z * kLog2e, t.w * kLog2e);
         }
-        dtb[ch] = G.dt_bias ? __ldg(G.dt_bias + c) : 0.f;
+        dtb[ch] = G.dt_bias ? __ldg(G.dt_bias + c) * kLog2e : 0.f;       // pre-scaled: softplus_scaled takes x * log2(e)
         Dc[ch] = G.D ? __ldg(G.D + c) : 0.f;
     }
 
@@ -757,6 +757,8 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
 #pragma unroll
         for (int q = 0; q < 4; ++q) { Bq[q] = bc[q]; Cq[q] = bc[4 + q]; }
         const int row_off = S.rows[buf][jj];
+        uint64_t ysum[CPL];
+        float uu_[CPL], zz_[CPL];
 #pragma unroll
         for (int ch = 0; ch < CPL; ++ch) {
             const float uu = to_f32<T>(S.us[buf][jj][ch * 32 + lane]);
@@ -791,12 +793,34 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
                     y1 = fma2(h[ch][2 * q + 1], Cq[q].y, y1);
                 }
             }
-            float ya, yb, yc, yd;
-            unpack2(y0, ya, yb);
-            unpack2(y1, yc, yd);
-            const float y = fmaf(Dc[ch], uu, (ya + yb) + (yc + yd));
-            const float o = y * (kSplit ? silu_fast(zz) : silu_tanh(zz));    // bf16 output: 1 MUFU (tanh) is enough
-            *reinterpret_cast<T*>(out_lane + row_off + ch * 32 * static_cast<int>(sizeof(T))) = from_f32<T>(o);
+            ysum[ch] = add2(y0, y1);                 // (y_even-pairs + y_odd-pairs): two partial sums per channel
+            uu_[ch] = uu;
+            zz_[ch] = zz;
+        }
+        if constexpr (CPL == 2 && !kSplit) {
+            // both channels of the lane at once on the packed-fp32 pipe: y = sum + D u ; out = y z (0.5 + 0.5 tanh(z/2))
+            float a0, a1, b0, b1;
+            unpack2(ysum[0], a0, a1);
+            unpack2(ysum[1], b0, b1);
+            const uint64_t u2 = pack2(uu_[0], uu_[1]), z2 = pack2(zz_[0], zz_[1]);
+            const uint64_t y2 = fma2(pack2(Dc[0], Dc[1]), u2, pack2(a0 + a1, b0 + b1));
+            const uint64_t half2 = pack2(0.5f, 0.5f);
+            float hz0, hz1;
+            unpack2(mul2(z2, half2), hz0, hz1);
+            const uint64_t sg = fma2(pack2(tanh_approx(hz0), tanh_approx(hz1)), half2, half2);
+            float o0, o1;
+            unpack2(mul2(mul2(y2, z2), sg), o0, o1);
+            *reinterpret_cast<T*>(out_lane + row_off) = from_f32<T>(o0);
+            *reinterpret_cast<T*>(out_lane + row_off + 32 * static_cast<int>(sizeof(T))) = from_f32<T>(o1);
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < CPL; ++ch) {
+                float ya, yb;
+                unpack2(ysum[ch], ya, yb);
+                const float y = fmaf(Dc[ch], uu_[ch], ya + yb);
+                const float o = y * (kSplit ? silu_fast(zz_[ch]) : silu_tanh(zz_[ch]));   // bf16 output: 1 MUFU (tanh) is enough
+                *reinterpret_cast<T*>(out_lane + row_off + ch * 32 * static_cast<int>(sizeof(T))) = from_f32<T>(o);
+            }
         }
     };
 
@@ -820,48 +844,50 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
         }
         __syncwarp();
 
-        // ---- delta_raw tile (8 tokens x 64 channels) = dt_low (8 x 32) . W_dt^T on mma.sync; rows 8..15 of the
-        //      m16 tile are fed zeros ----
+        // ---- delta_raw tile (64 channels x 8 tokens) = W_dt slice (64 x 32) . dt_low^T (32 x 8) on mma.sync m16n8k16:
+        //      A = 16 channels x 16 k from shared (ldmatrix), B = the chunk's dt_low rows straight from the staged
+        //      x_dbl (token = lane / 4, k pair = lane % 4: exactly the B fragment), hi + lo halves of dt_low ----
         {
             const int r = lane >> 2, q = lane & 3;
             const uint32_t* row = reinterpret_cast<const uint32_t*>(&S.xd[buf][r][0]);   // 16 hi words, 16 lo words
-            uint32_t a_hi[2][4], a_lo[2][4];
+            uint32_t b_hi[2][2], b_lo[2][2];
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-                a_hi[ks][0] = row[ks * 8 + q]; a_hi[ks][1] = 0u; a_hi[ks][2] = row[ks * 8 + 4 + q]; a_hi[ks][3] = 0u;
-                a_lo[ks][0] = row[16 + ks * 8 + q]; a_lo[ks][1] = 0u; a_lo[ks][2] = row[16 + ks * 8 + 4 + q]; a_lo[ks][3] = 0u;
+                b_hi[ks][0] = row[ks * 8 + q]; b_hi[ks][1] = row[ks * 8 + 4 + q];
+                b_lo[ks][0] = row[16 + ks * 8 + q]; b_lo[ks][1] = row[16 + ks * 8 + 4 + q];
             }
+            constexpr int kMT = kSC / 16;                    // 16-channel tiles: 4 (2 ch/lane) or 2
+            float dacc[kMT][4];
 #pragma unroll
-            // 4 n-tiles at a time, MMA chains interleaved (4 independent accumulators in flight)
+            for (int t = 0; t < kMT; ++t)
 #pragma unroll
-            for (int half = 0; half < kSC / 32; ++half) {
-                float dacc[4][4];
-                uint32_t bw[4][4];
+                for (int i = 0; i < 4; ++i) dacc[t][i] = 0.f;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t aw[kMT][4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) dacc[t][i] = 0.f;
-                    ldmatrix_x4_u(bw[t], smem_u32(&S.wdt[0][(half * 4 + t) * 8 + (lane & 7)][(lane >> 3) * 8]));
-                }
+                for (int t = 0; t < kMT; ++t)
+                    ldmatrix_x4_u(aw[t], smem_u32(&S.wdt[0][t * 16 + (lane & 15)][ks * 16 + (lane >> 4) * 8]));
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
+                for (int t = 0; t < kMT; ++t) mma_nv(dacc[t], aw[t], b_hi[ks][0], b_hi[ks][1]);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) mma_nv(dacc[t], a_hi[ks], bw[t][2 * ks], bw[t][2 * ks + 1]);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) mma_nv(dacc[t], a_lo[ks], bw[t][2 * ks], bw[t][2 * ks + 1]);
-                }
+                for (int t = 0; t < kMT; ++t) mma_nv(dacc[t], aw[t], b_lo[ks][0], b_lo[ks][1]);
                 if constexpr (kSplit) {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        ldmatrix_x4_u(bw[t], smem_u32(&S.wdt[kSplit ? 1 : 0][(half * 4 + t) * 8 + (lane & 7)][(lane >> 3) * 8]));
+                    for (int t = 0; t < kMT; ++t)
+                        ldmatrix_x4_u(aw[t], smem_u32(&S.wdt[1][t * 16 + (lane & 15)][ks * 16 + (lane >> 4) * 8]));
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) mma_nv(dacc[t], a_hi[ks], bw[t][2 * ks], bw[t][2 * ks + 1]);
+                    for (int t = 0; t < kMT; ++t) mma_nv(dacc[t], aw[t], b_hi[ks][0], b_hi[ks][1]);
                 }
+            }
+            // accumulator (channel = 16 t + r [+ 8], tokens 2q, 2q + 1) -> ds[token][channel]; the 68-word pitch keeps
+            // the 32 lanes of each store on 32 different banks
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    *reinterpret_cast<float2*>(&S.ds[r][(half * 4 + t) * 8 + 2 * q]) = make_float2(dacc[t][0], dacc[t][1]);
+            for (int t = 0; t < kMT; ++t) {
+                S.ds[2 * q][t * 16 + r] = dacc[t][0];
+                S.ds[2 * q + 1][t * 16 + r] = dacc[t][1];
+                S.ds[2 * q][t * 16 + r + 8] = dacc[t][2];
+                S.ds[2 * q + 1][t * 16 + r + 8] = dacc[t][3];
             }
         }
         __syncwarp();
@@ -873,7 +899,7 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
 #pragma unroll
             for (int jj = 0; jj < kCH; ++jj)
 #pragma unroll
-                for (int ch = 0; ch < CPL; ++ch) dtv[jj][ch] = softplus_fast(S.ds[jj][ch * 32 + lane] + dtb[ch]);
+                for (int ch = 0; ch < CPL; ++ch) dtv[jj][ch] = softplus_scaled(fmaf(S.ds[jj][ch * 32 + lane], kLog2e, dtb[ch]));
 #pragma unroll
             for (int jj = 0; jj < kCH; ++jj) token(buf, jj, dtv[jj]);
         } else {
@@ -882,7 +908,7 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
             for (int jj = 0; jj < nrows; ++jj) {
                 float dtv[CPL];
 #pragma unroll
-                for (int ch = 0; ch < CPL; ++ch) dtv[ch] = softplus_fast(S.ds[jj][ch * 32 + lane] + dtb[ch]);
+                for (int ch = 0; ch < CPL; ++ch) dtv[ch] = softplus_scaled(fmaf(S.ds[jj][ch * 32 + lane], kLog2e, dtb[ch]));
                 token(buf, jj, dtv);
             }
         }
