@@ -176,8 +176,7 @@ def s6_backward_cuda(u, z_src, dt_raw, Bm, Cm, A_h, D_h, dtb_h, dv, plan, nheads
     x_dbl[..., R:R + N] = Bm
     x_dbl[..., R + N:] = Cm
     head = torch.arange(D, device=dev) // P
-    onehot = torch.zeros((D, R), **f32)
-    onehot[torch.arange(D, device=dev), head] = 1.0
+    onehot = (torch.arange(R, device=dev)[None, :] == head[:, None]).to(torch.float32)      # no host scalar: graph-capturable
     xz, weights = [], []
     for g in range(G):
         t = torch.zeros((B, plan.src_len, 2 * D), dtype=act, device=dev)

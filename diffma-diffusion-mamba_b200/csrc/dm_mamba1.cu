@@ -300,14 +300,29 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
     const int tiles_per_seq = (L + kTP2 - 1) / kTP2;
     const bool has_order = p.order != nullptr;
 
-    auto decode = [&](int tile, int& g, int& b, int& k, int& j0) {
+    // tile -> (mixer g, batch b, direction k, first token j0).  Decoded once per CTA with divisions, then advanced
+    // incrementally: the runtime divisions cost ~250 instructions per thread and tile in the first version
+    struct TilePos { int g, b, k, j0; };
+    auto decode = [&](int tile) {
+        TilePos t;
         const int seq = tile / tiles_per_seq;
-        j0 = (tile - seq * tiles_per_seq) * kTP2;
-        k = seq % p.K; b = (seq / p.K) % p.B; g = seq / (p.K * p.B);
+        t.j0 = (tile - seq * tiles_per_seq) * kTP2;
+        t.k = seq % p.K; t.b = (seq / p.K) % p.B; t.g = seq / (p.K * p.B);
+        return t;
     };
-    auto load_tile = [&](int tile, int buf) {
-        int g, b, k, j0;
-        decode(tile, g, b, k, j0);
+    auto advance = [&](TilePos t) {
+        t.j0 += kTP2;
+        if (t.j0 >= L) {
+            t.j0 = 0;
+            if (++t.k == p.K) {
+                t.k = 0;
+                if (++t.b == p.B) { t.b = 0; ++t.g; }
+            }
+        }
+        return t;
+    };
+    auto load_tile = [&](const TilePos& tp, int buf) {
+        const int g = tp.g, b = tp.b, k = tp.k, j0 = tp.j0;
         const M1G& G = p.g[g];
         const int32_t* ord = has_order ? ord_s + k * L : nullptr;
         const T* x_base = static_cast<const T*>(G.xz) + static_cast<int64_t>(b) * G.xz_bs;
@@ -363,20 +378,16 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
         __syncthreads();
     }
     int tile = tile_lo;
-    {
-        int g, b, k, j0;
-        decode(tile, g, b, k, j0);
-        load_group(g);
-        load_tile(tile, 0);
-        cp_async_commit();
-    }
+    TilePos cur = decode(tile);
+    load_group(cur.g);
+    load_tile(cur, 0);
+    cp_async_commit();
     int buf = 0;
     for (; tile < tile_hi; ++tile, buf ^= 1) {
-        int g, b, k, j0;
-        decode(tile, g, b, k, j0);
+        const int g = cur.g, b = cur.b, k = cur.k, j0 = cur.j0;
         const M1G& G = p.g[g];
-        const int next = tile + 1;
-        if (next < tile_hi) load_tile(next, buf ^ 1);
+        const TilePos nxt = advance(cur);
+        if (tile + 1 < tile_hi) load_tile(nxt, buf ^ 1);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
@@ -475,6 +486,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
             }
         }
         __syncthreads();                                   // reduce buffer free before the next prefetch lands in it
+        cur = nxt;
     }
 }
 

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--model", default="DiffMa-XL/4")
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--mamba2", action="store_true", help="train with the Mamba-2 mixers (reference: train.py --use-mamba2)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
@@ -47,7 +48,7 @@ def main():
     from diffma_b200 import _cabi, create_model_and_diffusion, ops, synth
     _cabi.lib()
     torch.manual_seed(rank)                       # train.py:99 seeds per rank
-    net, diffusion = create_model_and_diffusion(args.model, respacing="")
+    net, diffusion = create_model_and_diffusion(args.model, use_mamba2=args.mamba2, respacing="")
     synth.fill_trained_like_(net, seed=11)
     net = net.to(device).train()
     ema = None
@@ -135,7 +136,7 @@ def main():
             "metric": "training_images_per_s", "value": round(world * args.batch * args.steps / sec, 2), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(sec / args.steps * 1e3, 3),
             "higher_is_better": True, "scaling": "weak", "dtype": "f32" if args.fp32 else "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.model} training step (fwd+bwd+{'DDP all-reduce+' if world > 1 else ''}AdamW), "
+            "config": {"workload": f"{args.model}{' --use-mamba2' if args.mamba2 else ''} training step (fwd+bwd+{'DDP all-reduce+' if world > 1 else ''}AdamW), "
                                    f"L={L}, per-GPU batch {args.batch}", "global_batch": world * args.batch,
                        "grad_allreduce_mib": round(nparam * 4 / 2 ** 20, 1)},
             "loss": round(float(loss.item()), 5), "cuda_graph": graph is not None}), flush=True)
