@@ -9,7 +9,8 @@ synthetic latents, bf16 autocast, captured as a CUDA graph.  N>1 (torchrun): eve
 batch on its own latents (weak scaling, no data-path collective -- sampling shards by batch).
 
 ``value``       device-resident images/s over all ranks (CUDA events, barrier + synchronize both sides, max over ranks)
-``e2e``         same step through the public API with HOST (pinned) inputs: H2D of x/t/y/y2/w, step, D2H of the sample
+``e2e``         same step through the public API with HOST (pinned) inputs: H2D of x/t/y/y2/w, step, D2H of the sample;
+                inputs and results double buffered, the host consumes every sample one step behind the device
 ``roofline``    the dominant kernel (m1_scan_kernel / m2_ssd_kernel) timed alone at the workload's shape with L2 flushes
 ``cpu_baseline`` the oracle (restatement of the reference's CPU selective_scan_ref path) on the host cores, N=1 only
 ``--impl reference``  times that CPU path with all host threads on a bounded sample per step.
@@ -388,9 +389,14 @@ def main():
     kw_host = {"y": host["y"], "y2": host["y2"], "w": host["w"]}
     main = torch.cuda.current_stream(device)
 
+    out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+
     def e2e_run(n):
         # every step: H2D of that step's pinned inputs (double buffered: the copy of step i+1 travels on a copy stream
-        # while step i computes), the step, D2H of the step's sample, host sync on the result
+        # while step i computes), the step, D2H of the step's sample into a pinned buffer.  The host waits for EVERY
+        # step's result, one step behind the device (results double buffered too): a serving loop consumes sample i
+        # while step i+1 is already queued, so launch latency does not idle the GPU.
         sampler.prefetch(0, host["x"], t_host, kw_host)
         for i in range(n):
             s = i & 1
@@ -398,8 +404,11 @@ def main():
             if i + 1 < n:
                 sampler.prefetch(1 - s, host["x"], t_host, kw_host)
             sampler.step()
-            out_host.copy_(sampler.x, non_blocking=True)
-            main.synchronize()
+            out_hosts[s].copy_(sampler.x, non_blocking=True)
+            done[s].record(main)
+            if i > 0:
+                done[1 - s].synchronize()              # sample i-1 is on the host now
+        done[(n - 1) & 1].synchronize()
 
     e2e_run(3)
     barrier(world)

@@ -27,9 +27,10 @@ step = launches[a:b]
 
 def short(n):
     n = re.sub(r"^void ", "", n)
+    n = n.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
     n = re.sub(r"\(.*", "", n)
     n = re.sub(r"<.*", "", n)
-    return n.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+    return n
 
 
 agg = collections.OrderedDict()
