@@ -15,7 +15,7 @@ DM_F32, DM_BF16 = 0, 1
 DM_MAX_GROUPS = 4
 DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
-EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
+EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba1_bwd_chunk_tokens", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
            "dm_spiral_post_mix", "dm_gemm_bf16_tn", "dm_p_sample_update", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     L.dm_mamba1_sched_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     L.dm_mamba1_scan_phase.restype = C.c_int
     L.dm_mamba1_scan_phase.argtypes = [C.POINTER(Mamba1Args), C.c_int, C.c_void_p]
+    L.dm_mamba1_bwd_chunk_tokens.restype = C.c_int
     L.dm_mamba1_scan_bwd.restype = C.c_int
     L.dm_mamba1_scan_bwd.argtypes = [C.POINTER(Mamba1Args), C.POINTER(Mamba1BwdGroup), C.c_int, C.c_void_p]
     L.dm_mamba2_ssd_fwd.restype = C.c_int

@@ -95,7 +95,8 @@ class Mamba1ScanFn(torch.autograd.Function):
         dout = dout.to(x0.dtype).contiguous()
         a, _ = ops.mamba1_args(xz, weights, plan, bufs=(dout, u, x_dbl))
         f32 = dict(dtype=torch.float32, device=dev)
-        nch = (L + 7) // 8
+        ct = int(_cabi.lib().dm_mamba1_bwd_chunk_tokens())
+        nch = (L + ct - 1) // ct
         d_xz_scan = torch.empty((G, B, K, L, 2 * D), **f32)
         du = torch.empty((G, B, K, L, D), **f32)
         ddelta = torch.empty((G, B, K, L, D), **f32)
@@ -189,7 +190,8 @@ def s6_backward_cuda(u, z_src, dt_raw, Bm, Cm, A_h, D_h, dtb_h, dv, plan, nheads
             A=A_h[g].float()[head].unsqueeze(1).expand(D, N).contiguous(),
             D=None if D_h[g] is None else D_h[g].float()[head].contiguous()))
     a, _ = ops.mamba1_args(xz, weights, plan, bufs=(dv.contiguous(), u.contiguous(), x_dbl))
-    nch = (L + 7) // 8
+    ct = int(_cabi.lib().dm_mamba1_bwd_chunk_tokens())
+    nch = (L + ct - 1) // ct
     d_xz_scan = torch.zeros((G, B, K, L, 2 * D), **f32)
     du = torch.empty((G, B, K, L, D), **f32)
     ddelta = torch.empty((G, B, K, L, D), **f32)

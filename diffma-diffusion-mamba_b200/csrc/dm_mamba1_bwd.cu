@@ -3,7 +3,7 @@
 // reference through train.py:259).  Everything here works in SCAN order; the host un-permutes and sums directions.
 //
 //   m1_scan_bwd_kernel   one warp per (sequence, 32 channels), lane = channel.
-//        sweep 1 (forward): recompute the recurrence, store the state at every 8-token chunk boundary in a workspace
+//        sweep 1 (forward): recompute the recurrence, store the state at every chunk boundary (DM_BWD_CH = 4 tokens) in a workspace
 //        sweep 2 (reverse, chunk by chunk): reload the boundary state, recompute the chunk's states into shared
 //        memory, then run the adjoint recurrence  dh_{j-1} = a_j dh_j,  dh_j += dy_j C_j  backwards, producing
 //        dz, du (scan part), d(delta_raw) per token, dB/dC (reduced over the warp's 32 channels through a shared
@@ -18,7 +18,14 @@
 namespace dm {
 namespace {
 
-constexpr int kN = 16, kW = 4, kE = 64, kR = 32, kCH = 8;
+#ifndef DM_BWD_CH
+#define DM_BWD_CH 4           // tokens per backward chunk: 4 keeps the per-warp state buffer at 8 KB => 12 warps per SM
+#endif
+#ifndef DM_BWD_MINB
+#define DM_BWD_MINB 12
+#endif
+constexpr int kN = 16, kW = 4, kE = 64, kR = 32, kCH = DM_BWD_CH;
+constexpr int kMR = 8;        // rows of the dt_proj MMA tile (m16n8k16, 8 token rows used); xd / ds are sized for it
 
 struct B1G {
     const void* xz; int64_t xz_bs, xz_ts;
@@ -63,14 +70,14 @@ __device__ __forceinline__ const int32_t* dir_order(const B1P& p, int k) {
 
 template <typename T> struct BwdSmem {
     float hs[kCH][kN][32];       // state BEFORE each token of the chunk
-    float xd[kCH][kE];           // x_dbl rows of the chunk
-    float ds[kCH][34];           // delta_raw tile
+    float xd[2][kCH][kE];        // x_dbl rows of the chunk, double buffered (cp.async)
+    float ds[kMR][34];           // delta_raw tile (the MMA tile has 8 token rows; rows >= kCH are never read)
     float tb[32][33];            // transposition buffer for the dB / dC reduction over channels
-    T us[kCH][32], zs[kCH][32], dos[kCH][32];
+    T us[2][kCH][32], zs[2][kCH][32], dos[2][kCH][32];
 };
 
 template <typename T>
-__global__ void __launch_bounds__(32, 8) m1_scan_bwd_kernel(const __grid_constant__ B1P p, int n_units) {
+__global__ void __launch_bounds__(32, DM_BWD_MINB) m1_scan_bwd_kernel(const __grid_constant__ B1P p, int n_units) {
     constexpr bool kSplit = sizeof(T) == 4;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     BwdSmem<T>& S = *reinterpret_cast<BwdSmem<T>*>(smem_raw);
@@ -122,26 +129,49 @@ __global__ void __launch_bounds__(32, 8) m1_scan_bwd_kernel(const __grid_constan
             }
     }
 
-    // loads the x_dbl rows + u of chunk ci and leaves delta_raw of the chunk in S.ds (same MMA as the forward)
-    auto load_chunk = [&](int ci, bool with_grad) {
-        const int j0 = ci * kCH, nrows = min(kCH, L - j0);
-        __syncwarp();
-        for (int s = lane; s < kCH * (kE / 4); s += 32) {
-            const int r = s / (kE / 4), part = s % (kE / 4);
-            const int j = min(j0 + r, L - 1);
-            reinterpret_cast<float4*>(&S.xd[r][0])[part] =
-                __ldg(reinterpret_cast<const float4*>(xd_seq + static_cast<int64_t>(j) * kE) + part);
+    // Chunk staging, double buffered: issue() starts the cp.async copies of chunk ci (x_dbl rows, u, and for the reverse
+    // sweep z and dout, 16-byte segments straight to shared memory) and returns at once; finish() waits for the OLDEST
+    // outstanding group and leaves delta_raw of that chunk in S.ds (same MMA as the forward).  The next chunk's loads are
+    // always in flight while the current one is processed: the first version loaded synchronously and spent most of
+    // its time waiting on L2 with 2-3 warps per sub-partition.
+    constexpr int kEpS = 16 / static_cast<int>(sizeof(T));     // elements per 16-byte segment
+    constexpr int kSegRow = 32 / kEpS;                         // segments per (token, 32 channels) row
+    const T* u0 = u_seq - lane;
+    const T* z0 = z_base - lane;
+    const T* do0 = do_base - lane;
+    // source token of this lane's (row, segment) in the chunk the reverse sweep issues NEXT: read one chunk ahead, so
+    // the scan-order lookup never sits between issue() and its dependent copies
+    int src_pref = 0;
+    auto load_src = [&](int ci) {
+        if (ci >= 0 && lane < kCH * kSegRow) {
+            const int j = min(ci * kCH + lane / kSegRow, L - 1);
+            src_pref = ord ? __ldg(ord + j) : j;
         }
-#pragma unroll
-        for (int r = 0; r < kCH; ++r) {
+    };
+    auto issue = [&](int ci, int buf, bool with_grad) {
+        const int j0 = ci * kCH;
+        for (int sgm = lane; sgm < kCH * (kE / 4); sgm += 32) {
+            const int r = sgm / (kE / 4), part = sgm % (kE / 4);
             const int j = min(j0 + r, L - 1);
-            S.us[r][lane] = u_seq[static_cast<int64_t>(j) * D];
+            cp_async16(smem_u32(&S.xd[buf][r][part * 4]), xd_seq + static_cast<int64_t>(j) * kE + part * 4);
+        }
+        for (int sgm = lane; sgm < kCH * kSegRow; sgm += 32) {
+            const int r = sgm / kSegRow, part = sgm % kSegRow;
+            const int j = min(j0 + r, L - 1);
+            cp_async16(smem_u32(&S.us[buf][r][part * kEpS]), u0 + static_cast<int64_t>(j) * D + part * kEpS);
             if (with_grad) {
-                const int src = ord ? __ldg(ord + j) : j;
-                S.zs[r][lane] = z_base[static_cast<int64_t>(src) * G.xz_ts];
-                S.dos[r][lane] = (r < nrows) ? do_base[static_cast<int64_t>(token_order ? src : j) * G.do_ts] : from_f32<T>(0.f);
+                const int src = src_pref;                     // kCH * kSegRow <= 32: this loop runs once per lane
+                cp_async16(smem_u32(&S.zs[buf][r][part * kEpS]), z0 + static_cast<int64_t>(src) * G.xz_ts + part * kEpS);
+                cp_async16(smem_u32(&S.dos[buf][r][part * kEpS]),
+                           do0 + static_cast<int64_t>(token_order ? src : j) * G.do_ts + part * kEpS);
             }
         }
+        cp_async_commit();
+        if (with_grad) load_src(ci - 1);
+    };
+    static_assert(kCH * kSegRow <= 32, "one (row, segment) of u / z / dout per lane");
+    auto finish = [&](int buf, bool more_in_flight) {
+        if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncwarp();
         float dacc[4][4];
 #pragma unroll
@@ -149,7 +179,7 @@ __global__ void __launch_bounds__(32, 8) m1_scan_bwd_kernel(const __grid_constan
 #pragma unroll
             for (int i = 0; i < 4; ++i) dacc[nt][i] = 0.f;
         const int r = lane >> 2, q = lane & 3;
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(&S.xd[r][0]);
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(&S.xd[buf][r < kCH ? r : kCH - 1][0]);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
             const uint32_t a_hi[4] = {row[ks * 8 + q], 0u, row[ks * 8 + 4 + q], 0u};
@@ -171,17 +201,22 @@ __global__ void __launch_bounds__(32, 8) m1_scan_bwd_kernel(const __grid_constan
     float h[kN];
 #pragma unroll
     for (int n = 0; n < kN; ++n) h[n] = 0.f;
+    if (n_chunks > 1) issue(0, 0, false);
     for (int ci = 0; ci < n_chunks; ++ci) {
         float* hbc = hb + static_cast<int64_t>(ci) * D * kN;
 #pragma unroll
         for (int n = 0; n < kN; n += 4) *reinterpret_cast<float4*>(hbc + n) = make_float4(h[n], h[n + 1], h[n + 2], h[n + 3]);
         if (ci == n_chunks - 1) break;                       // the last chunk's end state is never needed
-        load_chunk(ci, false);
+        const int buf = ci & 1;
+        const bool more = ci + 1 < n_chunks - 1;             // sweep 1 visits chunks 0 .. n_chunks - 2
+        __syncwarp();                                        // every lane is done with the buffer the prefetch overwrites
+        if (more) issue(ci + 1, buf ^ 1, false);
+        finish(buf, more);
 #pragma unroll
         for (int jj = 0; jj < kCH; ++jj) {
             const float dt = softplus_fast(S.ds[jj][lane] + dtb);
-            const float dtu = dt * to_f32<T>(S.us[jj][lane]);
-            const float* Bv = &S.xd[jj][kR];
+            const float dtu = dt * to_f32<T>(S.us[buf][jj][lane]);
+            const float* Bv = &S.xd[buf][jj][kR];
 #pragma unroll
             for (int n = 0; n < kN; ++n) h[n] = fmaf(ex2_approx(dt * A2[n]), h[n], dtu * Bv[n]);
         }
@@ -196,9 +231,15 @@ __global__ void __launch_bounds__(32, 8) m1_scan_bwd_kernel(const __grid_constan
     float* du_out = G.du + sg * L * D + c;
     float* dd_out = G.ddelta + sg * L * D + c;
     float* dxd_out = G.d_x_dbl + sg * L * kE;
+    __syncwarp();
+    load_src(n_chunks - 1);
+    issue(n_chunks - 1, (n_chunks - 1) & 1, true);
     for (int ci = n_chunks - 1; ci >= 0; --ci) {
         const int j0 = ci * kCH, nrows = min(kCH, L - j0);
-        load_chunk(ci, true);
+        const int buf = ci & 1;
+        __syncwarp();                                        // every lane is done with the buffer the prefetch overwrites
+        if (ci > 0) issue(ci - 1, buf ^ 1, true);
+        finish(buf, ci > 0);
         const float* hbc = hb + static_cast<int64_t>(ci) * D * kN;
 #pragma unroll
         for (int n = 0; n < kN; n += 4) {
@@ -210,10 +251,10 @@ __global__ void __launch_bounds__(32, 8) m1_scan_bwd_kernel(const __grid_constan
 #pragma unroll
         for (int jj = 0; jj < kCH; ++jj) {
             const float dt = softplus_fast(S.ds[jj][lane] + dtb);
-            const float uu = to_f32<T>(S.us[jj][lane]);
+            const float uu = to_f32<T>(S.us[buf][jj][lane]);
             const float dtu = dt * uu;
-            const float* Bv = &S.xd[jj][kR];
-            const float* Cv = &S.xd[jj][kR + kN];
+            const float* Bv = &S.xd[buf][jj][kR];
+            const float* Cv = &S.xd[buf][jj][kR + kN];
             float y = 0.f;
 #pragma unroll
             for (int n = 0; n < kN; ++n) {
@@ -230,15 +271,15 @@ __global__ void __launch_bounds__(32, 8) m1_scan_bwd_kernel(const __grid_constan
             if (jj < nrows) {
                 const int j = j0 + jj;
                 const float dt = dtv[jj];
-                const float uu = to_f32<T>(S.us[jj][lane]);
-                const float zz = to_f32<T>(S.zs[jj][lane]);
-                const float go = to_f32<T>(S.dos[jj][lane]);
+                const float uu = to_f32<T>(S.us[buf][jj][lane]);
+                const float zz = to_f32<T>(S.zs[buf][jj][lane]);
+                const float go = to_f32<T>(S.dos[buf][jj][lane]);
                 const float sg_z = sigmoid_fast(zz);
                 const float dy = go * zz * sg_z;                                   // d out / d y = silu(z)
                 const float dz = go * yv[jj] * sg_z * fmaf(zz, 1.0f - sg_z, 1.0f);    // silu'(z) = s (1 + z (1 - s))
                 dD = fmaf(dy, uu, dD);
-                const float* Bv = &S.xd[jj][kR];
-                const float* Cv = &S.xd[jj][kR + kN];
+                const float* Bv = &S.xd[buf][jj][kR];
+                const float* Cv = &S.xd[buf][jj][kR + kN];
                 float ddt = 0.f, dbu = 0.f;     // d delta, sum_n dh_n B_n
                 float pB[kN], pC[kN];
 #pragma unroll
@@ -325,6 +366,8 @@ __global__ void __launch_bounds__(128) m1_conv_bwd_kernel(const __grid_constant_
 }  // namespace
 }  // namespace dm
 
+extern "C" int dm_mamba1_bwd_chunk_tokens(void) { return dm::kCH; }
+
 extern "C" int dm_mamba1_scan_bwd(const dm_mamba1_args* a, const dm_mamba1_bwd_group* gr, int phase, void* stream) {
     using namespace dm;
     if (a == nullptr || gr == nullptr) return DM_ERR_INVALID_ARG;
@@ -360,6 +403,7 @@ extern "C" int dm_mamba1_scan_bwd(const dm_mamba1_args* a, const dm_mamba1_bwd_g
             static thread_local bool cfg = false;
             if (!cfg) {
                 DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 cfg = true;
             }
             m1_scan_bwd_kernel<float><<<n_units, 32, bytes, st>>>(p, n_units);
@@ -368,6 +412,7 @@ extern "C" int dm_mamba1_scan_bwd(const dm_mamba1_args* a, const dm_mamba1_bwd_g
             static thread_local bool cfg = false;
             if (!cfg) {
                 DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 cfg = true;
             }
             m1_scan_bwd_kernel<__nv_bfloat16><<<n_units, 32, bytes, st>>>(p, n_units);

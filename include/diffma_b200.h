@@ -135,13 +135,14 @@ typedef struct {
     float* dA;                 /* (d_inner, d_state), accumulated                                                     */
     float* dD;                 /* (d_inner), accumulated, or NULL                                                     */
     float* d_dt_bias;          /* (d_inner), accumulated, or NULL                                                     */
-    float* state_workspace;    /* (B, n_dir, ceil(seqlen/8), d_inner, d_state) scratch                                 */
+    float* state_workspace;    /* (B, n_dir, ceil(seqlen/c), d_inner, d_state) scratch, c = dm_mamba1_bwd_chunk_tokens() */
     float* d_conv_weight;      /* (d_inner, d_conv), accumulated                                                      */
     float* d_conv_bias;        /* (d_inner), accumulated, or NULL                                                     */
 } dm_mamba1_bwd_group;
 
 int dm_mamba1_scan_bwd(const dm_mamba1_args* args, const dm_mamba1_bwd_group* grads /* [n_groups] */, int phase,
                        void* stream);
+int dm_mamba1_bwd_chunk_tokens(void);     /* tokens between two saved states of `state_workspace` (4 in this build) */
 
 /* ------------------------------------------------------------------------------------------------------
  * Mamba-2 forward: split [z | x | B | C | dt] -> causal conv1d + SiLU over [x|B|C] -> softplus(dt + bias)
