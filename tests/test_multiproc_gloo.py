@@ -85,6 +85,68 @@ def test_ddp_gloo_gradients_equal_single_process():
         torch.testing.assert_close(torch.from_numpy(a), p.grad, rtol=1e-5, atol=1e-6)
 
 
+def _flat_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from diffma_b200.ddp import FlatGradSync
+    from diffma_b200.diffusion import create_diffusion
+    torch.manual_seed(rank)                       # different initial weights per rank: the broadcast must fix that
+    net = _Tiny()
+    sync = FlatGradSync(net.parameters(), world)
+    d = create_diffusion("")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 4, 8, 8, generator=g)
+    noise = torch.randn(4, 4, 8, 8, generator=g)
+    y = torch.randn(4, 16, generator=g)
+    t = torch.tensor([3, 250, 600, 999])
+    sl = slice(rank * 2, rank * 2 + 2)
+    out = []
+    with torch.enable_grad():
+        for _ in range(2):                        # second pass: zero() really clears, views survive a step
+            sync.zero()
+            d.training_losses(net, x[sl], t[sl], dict(y=y[sl], y2=None, w=None), noise=noise[sl])["loss"].mean().backward()
+            sync.check_views()
+            sync.allreduce()
+            out.append([p.grad.clone().numpy() for p in net.parameters()])
+    if rank == 0:
+        q.put((out, [p.detach().clone().numpy() for p in net.parameters()]))
+    dist.destroy_process_group()
+
+
+def test_flat_grad_sync_equals_single_process_gradient():
+    """diffma_b200.ddp.FlatGradSync (graph-friendly DDP: .grad views into one flat buffer, one all-reduce) averages
+    gradients exactly like DDP: the 2-rank result equals the single-process gradient on the concatenated batch, and
+    rank 0's weights were broadcast."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + os.getpid() % 200
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out, weights = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, ROOT)
+    from diffma_b200.diffusion import create_diffusion
+    torch.manual_seed(0)
+    net = _Tiny()                                  # rank 0's initial weights
+    for w, p in zip(weights, net.parameters()):
+        torch.testing.assert_close(torch.from_numpy(w), p.detach())
+    d = create_diffusion("")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 4, 8, 8, generator=g)
+    noise = torch.randn(4, 4, 8, 8, generator=g)
+    y = torch.randn(4, 16, generator=g)
+    t = torch.tensor([3, 250, 600, 999])
+    with torch.enable_grad():
+        d.training_losses(net, x, t, dict(y=y, y2=None, w=None), noise=noise)["loss"].mean().backward()
+    for step_grads in out:
+        for a, p in zip(step_grads, net.parameters()):
+            torch.testing.assert_close(torch.from_numpy(a), p.grad, rtol=1e-5, atol=1e-6)
+
+
 def test_reference_arm_under_torchrun_prints_once():
     env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",

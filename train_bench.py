@@ -31,10 +31,13 @@ def main():
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--mamba2", action="store_true", help="train with the Mamba-2 mixers (reference: train.py --use-mamba2)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--torch-ddp", action="store_true",
+                    help="multi-GPU: use torch DistributedDataParallel launched eagerly (host-bound) instead of "
+                         "diffma_b200.ddp.FlatGradSync between two CUDA graphs")
     args = ap.parse_args()
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        # DDP's NCCL all-reduce inside a whole-step capture deadlocked on this stack (torch 2.11 / NCCL 2.28): multi-GPU
-        # steps are launched eagerly (host-bound); the single-GPU step is one CUDA graph
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.torch_ddp:
+        # DDP's reducer hooks inside a whole-step capture deadlocked on this stack (torch 2.11 / NCCL 2.28): with torch
+        # DDP the multi-GPU step is launched eagerly
         args.no_graph = True
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -51,16 +54,19 @@ def main():
     net, diffusion = create_model_and_diffusion(args.model, use_mamba2=args.mamba2, respacing="")
     synth.fill_trained_like_(net, seed=11)
     net = net.to(device).train()
-    ema = None
     model = net
     side = torch.cuda.Stream(device=device)
-    if world > 1:
-        # DDP is built (and warmed up, below) on the side stream the graph capture will run on: its AccumulateGrad /
-        # bucket hooks remember the stream they were created under (torch's DDP + CUDA graphs recipe)
+    sync = None
+    if world > 1 and args.torch_ddp:
+        # DDP is built (and warmed up, below) on the side stream: its AccumulateGrad / bucket hooks remember the stream
+        # they were created under
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True)
         torch.cuda.current_stream(device).wait_stream(side)
+    elif world > 1:
+        from diffma_b200.ddp import FlatGradSync
+        sync = FlatGradSync(net.parameters(), world)         # same semantics as DDP; see diffma_b200/ddp.py
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0, fused=True, capturable=not args.no_graph)
     patch = int(args.model.split("/")[1])
     L = (28 // patch) ** 2
@@ -71,45 +77,68 @@ def main():
     noise_buf = torch.zeros_like(b["x"])
     loss_buf = torch.zeros((), device=device)
 
-    def body():
+    def fwd_bwd():
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not args.fp32):
             loss = diffusion.training_losses(model, b["x"], t_buf, kw, noise=noise_buf)["loss"].mean()
-        opt.zero_grad(set_to_none=True)
+        if sync is not None:
+            sync.zero()                                  # grads are views into one flat buffer: one memset, views stay
+        else:
+            opt.zero_grad(set_to_none=True)
         loss.backward()
-        opt.step()
         loss_buf.copy_(loss.detach())
 
-    graph = None
+    def body():
+        fwd_bwd()
+        if sync is not None:
+            sync.allreduce()
+        opt.step()
+
+    graph = graph_opt = None
 
     def step():
         # fresh timesteps / noise every step, drawn outside the graph into static buffers (train.py:243, q_sample)
         t_buf.copy_(torch.randint(0, diffusion.num_timesteps, (args.batch,), device=device, generator=g))
         noise_buf.normal_(generator=g)
-        if graph is not None:
-            graph.replay()
-        else:
+        if graph is None:
             body()
+        elif sync is None:
+            graph.replay()                               # whole step: forward, backward, fused AdamW
+        else:
+            graph.replay()                               # forward + backward into the flat gradient buffer
+            sync.allreduce()                             # ONE eager NCCL all-reduce (NVLink / NVSwitch)
+            graph_opt.replay()                           # fused AdamW
         return loss_buf
 
     if not args.no_graph:
-        # the whole step (forward, backward incl. dm_mamba1_scan_bwd, DDP all-reduce, fused AdamW) is one CUDA graph:
-        # the eager step is host-bound (~6000 launches for XL/4)
+        # single GPU: the whole step (forward, backward incl. dm_mamba1_scan_bwd, fused AdamW) is one CUDA graph -- the
+        # eager step is host-bound (~5000 launches for XL/4).  Multi-GPU: two graphs around one eager all-reduce.
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
-            for _ in range(11 if world > 1 else 3):
+            for _ in range(3):
                 step()
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
-        graph = torch.cuda.CUDAGraph()
-        opt.zero_grad(set_to_none=True)
         try:
-            with torch.cuda.graph(graph, stream=side):
-                body()
-        except RuntimeError as e:       # capture refused (e.g. a DDP/NCCL combination that cannot be captured): run eagerly
+            g1 = torch.cuda.CUDAGraph()
+            if sync is None:
+                opt.zero_grad(set_to_none=True)
+                with torch.cuda.graph(g1, stream=side):
+                    fwd_bwd()
+                    opt.step()
+                graph = g1
+            else:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, stream=side):
+                    fwd_bwd()
+                sync.check_views()
+                with torch.cuda.graph(g2, stream=side):
+                    opt.step()
+                graph, graph_opt = g1, g2
+        except RuntimeError as e:       # capture refused: run eagerly
             if rank == 0:
                 print(f"train_bench: CUDA-graph capture failed ({str(e).splitlines()[0]}); falling back to eager steps",
                       file=sys.stderr)
-            graph = None
+            graph = graph_opt = None
             torch.cuda.synchronize(device)
 
     for _ in range(max(3, args.warmup)):
@@ -139,7 +168,10 @@ def main():
             "config": {"workload": f"{args.model}{' --use-mamba2' if args.mamba2 else ''} training step (fwd+bwd+{'DDP all-reduce+' if world > 1 else ''}AdamW), "
                                    f"L={L}, per-GPU batch {args.batch}", "global_batch": world * args.batch,
                        "grad_allreduce_mib": round(nparam * 4 / 2 ** 20, 1)},
-            "loss": round(float(loss.item()), 5), "cuda_graph": graph is not None}), flush=True)
+            "loss": round(float(loss.item()), 5), "cuda_graph": graph is not None,
+            "grad_sync": "none" if world == 1 else ("torch DDP (eager)" if args.torch_ddp else
+                                                      "FlatGradSync: graph(fwd+bwd) -> 1 NCCL all-reduce -> graph(AdamW)")}),
+              flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
