@@ -16,7 +16,7 @@ DM_MAX_GROUPS = 4
 DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
 EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba1_bwd_chunk_tokens", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
-           "dm_spiral_post_mix", "dm_gemm_bf16_tn", "dm_p_sample_update", "dm_version", "dm_status_string", "dm_last_cuda_error",
+           "dm_spiral_post_mix", "dm_spiral_post_mix_pre", "dm_gemm_bf16_tn", "dm_p_sample_update", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
 
@@ -109,6 +109,9 @@ def lib() -> C.CDLL:
     L.dm_spiral_post_ln.argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, vp]
     L.dm_spiral_post_mix.restype = C.c_int
     L.dm_spiral_post_mix.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, vp]
+    L.dm_spiral_post_mix_pre.restype = C.c_int
+    L.dm_spiral_post_mix_pre.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, f32,
+                                         i32, vp]
     L.dm_gemm_bf16_tn.restype = C.c_int
     L.dm_gemm_bf16_tn.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i32, vp]
     L.dm_p_sample_update.restype = C.c_int

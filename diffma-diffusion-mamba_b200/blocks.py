@@ -114,20 +114,33 @@ class Spiral_MambaBlock(nn.Module):
 
     def _forward_fused(self, x, c, w, skip=None, mod=None):
         from . import ops
-        from .mixer import Mamba2, _act_dtype
+        from .mixer import _act_dtype
         B, L, D = x.shape
         act = _act_dtype(x)
         W = self._fused_weights(act)
-        m1, m2 = self.mamba1, self.mamba2
-        is_m2 = isinstance(m1, Mamba2)
         with torch.autocast("cuda", enabled=False):
             if mod is None:
                 mod = F.linear(F.silu(c.float()).to(act), W["ada_w"], W["ada_b"]).float()       # (B, 3D)
             wrow = None if w is None else w.reshape(B * L).float().contiguous()
             x2 = ops.spiral_pre(x, skip, W["ln1"][0], W["ln1"][1], mod, wrow, act)            # (2, B*L, D)
+            ab, hidden = self._fused_core(x2, B, L, act)
+            return ops.spiral_post_mix(x, skip, ab, hidden, W["w3"], W["b3"], mod)
+
+    def _fused_core(self, x2, B, L, act):
+        """The part of the block between the two row kernels: in_proj GEMM -> all directions of both mixers (one scan
+        launch pair) -> merge + out_proj GEMM -> LN(cat(a, b)) -> attention_network[1].  x2 (2, B*L, D) is
+        ``spiral_pre``'s output; returns (ab (2, B*L, D), hidden (B*L, D)).  ``DiffMa.forward`` calls this directly so
+        that one row kernel (``spiral_post_mix_pre``) can close block i and open block i+1."""
+        from . import ops
+        from .mixer import Mamba2
+        W = self._fused_weights(act)
+        m1, m2 = self.mamba1, self.mamba2
+        is_m2 = isinstance(m1, Mamba2)
+        D = x2.shape[-1]
+        with torch.autocast("cuda", enabled=False):
             tc = act == torch.bfloat16 and _USE_TCGEN05_GEMM       # hand-written tcgen05 GEMM (dm_gemm_bf16_tn)
             proj = ops.gemm_bf16_tn(x2, W["w_in_nk"]) if tc else torch.bmm(x2, W["w_in"])     # (2, B*L, d_in_proj)
-            plan = m1.plan("spiral", L, x.device)
+            plan = m1.plan("spiral", L, x2.device)
             xs = [proj[0].view(B, L, -1), proj[1].view(B, L, -1)]
             if not is_m2:
                 y = ops.mamba1_scan(xs, [m1.scan_weights(act), m2.scan_weights(act)], plan)      # (2, B, L, K, d_inner)
@@ -145,7 +158,7 @@ class Spiral_MambaBlock(nn.Module):
                 ab = (o.view(2, B * L, K, D) * rstd.reshape(2, B * L, K, 1).to(act)).sum(2)
             lnab = ops.spiral_post_ln(ab, W["ln2"][0], W["ln2"][1])                              # (B*L, 2D)
             hidden = F.linear(lnab, W["att_w"], W["att_b"])                                      # (B*L, D)
-            return ops.spiral_post_mix(x, skip, ab, hidden, W["w3"], W["b3"], mod)
+            return ab, hidden
 
     def initialize_weights(self):
         self.apply(_basic_init)

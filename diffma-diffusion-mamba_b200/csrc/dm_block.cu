@@ -198,6 +198,95 @@ spiral_post_mix_kernel(const float* __restrict__ x, const float* __restrict__ sk
     }
 }
 
+// post_mix of block i fused with pre of block i+1 (or of the final layer): the new residual row never leaves the
+// registers between the two.  x_out = (x + skip) + gate (alpha a + (1 - alpha) b)   [block i, as spiral_post_mix]
+//                             out2  = modulate(LayerNorm(x_out + skip2)) [, * w]     [block i+1, as spiral_pre]
+template <typename T, int NV>
+__global__ void __launch_bounds__(kRowWarps * 32)
+spiral_post_mix_pre_kernel(const float* __restrict__ x, const float* __restrict__ skip, const T* __restrict__ ab,
+                           const T* __restrict__ hidden, const float* __restrict__ w3, const float* __restrict__ b3,
+                           const float* __restrict__ mod, int64_t mod_stride, float* __restrict__ x_out,
+                           const float* __restrict__ skip2, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                           const float* __restrict__ mod2, int64_t mod2_stride, const float* __restrict__ w,
+                           T* __restrict__ out2, int rows, int L, float eps) {
+    constexpr int D = NV * 256;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int b = row / L;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        float hv[8], wv[8];
+        V8<T>::load(hidden + static_cast<int64_t>(row) * D + c, hv);
+        V8<float>::load(w3 + c, wv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s = fmaf(silu_fast(hv[e]), wv[e], s);
+    }
+    const float alpha = sigmoid_fast(warp_sum(s) + __ldg(b3));
+    const float* gate = mod + static_cast<int64_t>(b) * mod_stride + 2 * D;
+    float v[NV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        const int64_t off = static_cast<int64_t>(row) * D + c;
+        float xa[8], av[8], bv[8], gv[8];
+        V8<float>::load(x + off, xa);
+        if (skip) {
+            float t[8];
+            V8<float>::load(skip + off, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xa[e] += t[e];
+        }
+        V8<T>::load(ab + off, av);
+        V8<T>::load(ab + static_cast<int64_t>(rows) * D + off, bv);
+        V8<float>::load(gate + c, gv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] = fmaf(gv[e], fmaf(alpha, av[e] - bv[e], bv[e]), xa[e]);
+        V8<float>::store(x_out + off, v[i]);
+        if (skip2) {
+            float t[8];
+            V8<float>::load(skip2 + off, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[i][e] += t[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[i][e];
+    }
+    const float mean = warp_sum(sum) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float d = v[i][e] - mean;
+            q = fmaf(d, d, q);
+        }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    const float wr = w ? __ldg(w + row) : 1.0f;
+    const float* shift = mod2 + static_cast<int64_t>(b) * mod2_stride;
+    const float* scale = shift + D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        float g[8], bb[8], sh[8], sc[8], o1[8], o2[8];
+        V8<float>::load(ln_w + c, g);
+        V8<float>::load(ln_b + c, bb);
+        V8<float>::load(shift + c, sh);
+        V8<float>::load(scale + c, sc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float n = fmaf((v[i][e] - mean) * rstd, g[e], bb[e]);
+            o1[e] = fmaf(n, 1.0f + sc[e], sh[e]);
+            o2[e] = o1[e] * wr;
+        }
+        V8<T>::store(out2 + static_cast<int64_t>(row) * D + c, o1);
+        V8<T>::store(out2 + (static_cast<int64_t>(rows) + row) * D + c, o2);
+    }
+}
+
 inline int row_grid(int rows) { return (rows + kRowWarps - 1) / kRowWarps; }
 
 }  // namespace
@@ -262,6 +351,38 @@ extern "C" int dm_spiral_post_mix(const float* x, const float* skip, const void*
         spiral_post_mix_kernel<float, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
             x, skip, static_cast<const float*>(ab), static_cast<const float*>(hidden), w3, b3, mod, mod_batch_stride,
             out, rows, seqlen);
+    else
+        return DM_ERR_UNSUPPORTED;
+    DM_CUDA_TRY(cudaGetLastError());
+    return DM_OK;
+}
+
+
+extern "C" int dm_spiral_post_mix_pre(const float* x, const float* skip, const void* ab, const void* hidden,
+                                      const float* w3, const float* b3, const float* mod, int64_t mod_batch_stride,
+                                      float* x_out, const float* skip_next, const float* ln_weight, const float* ln_bias,
+                                      const float* mod_next, int64_t mod_next_batch_stride, const float* w, void* out2,
+                                      int32_t batch, int32_t seqlen, int32_t d_model, float eps, int32_t act_dtype,
+                                      void* stream) {
+    if (!x || !ab || !hidden || !w3 || !b3 || !mod || !x_out || !ln_weight || !ln_bias || !mod_next || !out2 || batch <= 0 ||
+        seqlen <= 0)
+        return DM_ERR_INVALID_ARG;
+    if (d_model != 512) return DM_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(ab) || !aligned16(hidden) || !aligned16(x_out) || !aligned16(mod) || !aligned16(mod_next) ||
+        !aligned16(out2) || (skip && !aligned16(skip)) || (skip_next && !aligned16(skip_next)) || (mod_batch_stride % 4) ||
+        (mod_next_batch_stride % 4))
+        return DM_ERR_INVALID_ARG;
+    const int rows = batch * seqlen;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (act_dtype == DM_BF16)
+        spiral_post_mix_pre_kernel<__nv_bfloat16, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
+            x, skip, static_cast<const __nv_bfloat16*>(ab), static_cast<const __nv_bfloat16*>(hidden), w3, b3, mod,
+            mod_batch_stride, x_out, skip_next, ln_weight, ln_bias, mod_next, mod_next_batch_stride, w,
+            static_cast<__nv_bfloat16*>(out2), rows, seqlen, eps);
+    else if (act_dtype == DM_F32)
+        spiral_post_mix_pre_kernel<float, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
+            x, skip, static_cast<const float*>(ab), static_cast<const float*>(hidden), w3, b3, mod, mod_batch_stride, x_out,
+            skip_next, ln_weight, ln_bias, mod_next, mod_next_batch_stride, w, static_cast<float*>(out2), rows, seqlen, eps);
     else
         return DM_ERR_UNSUPPORTED;
     DM_CUDA_TRY(cudaGetLastError());

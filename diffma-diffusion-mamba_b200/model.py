@@ -216,16 +216,34 @@ class DiffMa(nn.Module):
             c = torch.cat((te + y, te + y2m), dim=1)
             act = _act_dtype(h)
             mods, fmod = self._fused_mods(c, act)
-            outs = []
-            for i in range(self.depth):
-                skip = outs[self.depth - i - 1] if (i > self.depth / 2) else None
-                h = self.blocks[i]._forward_fused(h, c, w, skip, mods[:, i])
-                outs.append(h)
-            # final layer: LN (no affine, eps 1e-6) + modulate through the same row kernel, then the small Linear
-            D = h.shape[-1]
+            B, L, D = h.shape
             ones, zeros = self._cached("fl_affine", [self.pos_embed], lambda: (torch.ones(D, device=h.device),
                                                                                torch.zeros(D, device=h.device)))
-            hn = ops.spiral_pre(h, None, ones, zeros, fmod, None, act, eps=1e-6)[0].view(h.shape)
+            wrow = None if w is None else w.reshape(B * L).float().contiguous()
+            # One row kernel opens block 0; after that ``spiral_post_mix_pre`` closes block i (sigmoid mix + gated
+            # residual, reference mamba_block.py:111-114) and opens block i+1 (long-skip add of model.py:290-292,
+            # LayerNorm, adaLN modulate, soft mask: mamba_block.py:101-105) -- or the final layer's LN + modulate
+            # (eps 1e-6, no affine, model.py:92-109) -- in one pass over the residual stream.
+            outs = []
+            skip = None
+            W0 = self.blocks[0]._fused_weights(act)
+            x2 = ops.spiral_pre(h, None, W0["ln1"][0], W0["ln1"][1], mods[:, 0], wrow, act)
+            for i in range(self.depth):
+                blk = self.blocks[i]
+                Wb = blk._fused_weights(act)
+                ab, hidden = blk._fused_core(x2, B, L, act)
+                if i + 1 < self.depth:
+                    j = i + 1
+                    skip_next = outs[self.depth - j - 1] if (j > self.depth / 2) else None
+                    Wn = self.blocks[j]._fused_weights(act)
+                    h, x2 = ops.spiral_post_mix_pre(h, skip, ab, hidden, Wb["w3"], Wb["b3"], mods[:, i], skip_next,
+                                                    Wn["ln1"][0], Wn["ln1"][1], mods[:, j], wrow)
+                    skip = skip_next
+                else:
+                    h, x2 = ops.spiral_post_mix_pre(h, skip, ab, hidden, Wb["w3"], Wb["b3"], mods[:, i], None,
+                                                    ones, zeros, fmod, None, eps=1e-6)
+                outs.append(h)
+            hn = x2[0].view(h.shape)
             with torch.autocast("cuda", enabled=False):
                 lw, lb = self._cached(f"fl_lin_{act}", [self.final_layer.linear.weight, self.final_layer.linear.bias],
                                       lambda: (self.final_layer.linear.weight.to(act).contiguous(),

@@ -521,6 +521,26 @@ def spiral_post_mix(x, skip, ab, hidden, w3, b3, mod) -> torch.Tensor:
     return out
 
 
+def spiral_post_mix_pre(x, skip, ab, hidden, w3, b3, mod, skip_next, ln_weight, ln_bias, mod_next, w, eps: float = 1e-5):
+    """``spiral_post_mix`` of one block and ``spiral_pre`` of the next (or of the final layer) in one launch.
+    Returns (x_new fp32 (B,L,D), out2 (2, B*L, D) in ab's dtype)."""
+    B, L, D = x.shape
+    x_out = torch.empty_like(x)
+    out2 = torch.empty((2, B * L, D), dtype=ab.dtype, device=x.device)
+    if not (ab.is_contiguous() and hidden.is_contiguous() and hidden.dtype == ab.dtype):
+        raise RuntimeError("spiral_post_mix_pre: ab / hidden must be contiguous and of the same dtype")
+    st = _cabi.lib().dm_spiral_post_mix_pre(
+        _f32c(x, "x").data_ptr(), None if skip is None else _f32c(skip, "skip").data_ptr(), ab.data_ptr(),
+        hidden.data_ptr(), _f32c(w3, "w3").data_ptr(), _f32c(b3, "b3").data_ptr(), _mod2d(mod).data_ptr(), mod.stride(0),
+        x_out.data_ptr(), None if skip_next is None else _f32c(skip_next, "skip_next").data_ptr(),
+        _f32c(ln_weight, "ln_weight").data_ptr(), _f32c(ln_bias, "ln_bias").data_ptr(), _mod2d(mod_next).data_ptr(),
+        mod_next.stride(0), None if w is None else _f32c(w, "w").data_ptr(), out2.data_ptr(), B, L, D, eps,
+        _dtype_code(ab), _stream_handle(x.device))
+    _cabi.check(st, "dm_spiral_post_mix_pre")
+    LAUNCH_COUNTER["kernels"] += 1
+    return x_out, out2
+
+
 def _mod2d(mod: torch.Tensor) -> torch.Tensor:
     """adaLN output (B, 3D) fp32, rows may be strided (a slice of the all-blocks GEMM), channels contiguous."""
     if mod.dtype != torch.float32 or mod.dim() != 2 or mod.stride(1) != 1 or not mod.is_cuda or mod.stride(0) % 4:

@@ -198,6 +198,14 @@ int dm_spiral_post_ln(const void* ab, const float* ln_weight, const float* ln_bi
 int dm_spiral_post_mix(const float* x, const float* skip, const void* ab, const void* hidden, const float* w3,
                        const float* b3, const float* mod, int64_t mod_batch_stride, float* out, int32_t batch,
                        int32_t seqlen, int32_t d_model, int32_t act_dtype, void* stream);
+/* dm_spiral_post_mix of block i and dm_spiral_pre of block i+1 (or of the final layer: ln_weight = 1, ln_bias = 0,
+ * eps 1e-6, w = NULL) in one pass over the row: x_out as dm_spiral_post_mix's `out`, out2 as dm_spiral_pre's `out2`
+ * computed from x_out (+ skip_next).  Saves one launch and one read of the residual stream per block boundary. */
+int dm_spiral_post_mix_pre(const float* x, const float* skip, const void* ab, const void* hidden, const float* w3,
+                           const float* b3, const float* mod, int64_t mod_batch_stride, float* x_out,
+                           const float* skip_next, const float* ln_weight, const float* ln_bias, const float* mod_next,
+                           int64_t mod_next_batch_stride, const float* w, void* out2, int32_t batch, int32_t seqlen,
+                           int32_t d_model, float eps, int32_t act_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * One reverse-diffusion update as one elementwise kernel (reference diffusion/gaussian_diffusion.py p_mean_variance
