@@ -47,3 +47,27 @@ def test_invalid_arguments_return_status_not_crash():
     a.d_state = 16
     assert lib.dm_mamba1_scan_fwd(ctypes.byref(a), None) == _cabi.DM_ERR_INVALID_ARG       # null group pointers
     assert lib.dm_status_string(_cabi.DM_ERR_UNSUPPORTED).startswith(b"unsupported")
+
+
+def test_new_entry_points_reject_bad_arguments():
+    """ABI 3 additions: scheduler workspace sizing / alignment, backward chunking, fused row kernel."""
+    from diffma_b200 import _cabi
+    lib = _cabi.lib()
+    assert lib.dm_version() == 3
+    # workspace: 64 B header + 64 queue slots and 4 KB of state per (sequence, 64-channel) unit
+    units = 2 * 16 * 3 * (1024 // 64)
+    need = lib.dm_mamba1_sched_workspace_bytes(16, 3, 1024, 2)
+    assert need >= units * 4096 + units * 64 * 4 and need % 256 == 0
+    assert lib.dm_mamba1_sched_workspace_bytes(0, 3, 1024, 2) == 0
+    assert lib.dm_mamba1_bwd_chunk_tokens() in (4, 8)
+    a = _cabi.Mamba1Args()
+    a.batch = a.n_dir = a.seqlen = a.n_groups = 1
+    a.out_order, a.act_dtype, a.d_state, a.d_conv, a.dt_rank, a.d_inner = 0, _cabi.DM_BF16, 16, 4, 32, 1024
+    a.sched_workspace, a.sched_workspace_bytes = 8, 1 << 20          # misaligned scratch pointer
+    assert lib.dm_mamba1_scan_fwd(ctypes.byref(a), None) == _cabi.DM_ERR_INVALID_ARG
+    # fused row kernel: null pointers / unsupported width are statuses, not crashes
+    assert lib.dm_spiral_post_mix_pre(None, None, None, None, None, None, None, 0, None, None, None, None, None, 0, None,
+                                      None, 1, 1, 512, 1e-5, _cabi.DM_BF16, None) == _cabi.DM_ERR_INVALID_ARG
+    p = ctypes.c_void_p(1 << 12)
+    assert lib.dm_spiral_post_mix_pre(p, None, p, p, p, p, p, 1536, p, None, p, p, p, 1536, None, p, 1, 1, 384, 1e-5,
+                                      _cabi.DM_BF16, None) == _cabi.DM_ERR_UNSUPPORTED
