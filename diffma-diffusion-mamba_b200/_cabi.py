@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-DM_ABI_VERSION = 3
+DM_ABI_VERSION = 4
 DM_OK, DM_ERR_INVALID_ARG, DM_ERR_UNSUPPORTED, DM_ERR_CUDA = 0, -1, -2, -4
 DM_F32, DM_BF16 = 0, 1
 DM_MAX_GROUPS = 4
@@ -28,6 +28,7 @@ class Mamba1Group(C.Structure):
         ("u", C.c_void_p), ("x_dbl", C.c_void_p),
         ("conv_weight", C.c_void_p), ("conv_bias", C.c_void_p), ("x_proj_weight", C.c_void_p),
         ("dt_proj_weight", C.c_void_p), ("dt_bias", C.c_void_p), ("A", C.c_void_p), ("D", C.c_void_p),
+        ("chunk_states", C.c_void_p),
     ]
 
 
@@ -44,7 +45,7 @@ class Mamba1Args(C.Structure):
 
 class Mamba1BwdGroup(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("dout", "d_xz_scan", "du", "ddelta", "d_x_dbl", "dA", "dD", "d_dt_bias",
-                                          "state_workspace", "d_conv_weight", "d_conv_bias")]
+                                          "state_workspace", "d_conv_weight", "d_conv_bias")] + [("states_valid", C.c_int64)]
 
 
 class Mamba2Group(C.Structure):

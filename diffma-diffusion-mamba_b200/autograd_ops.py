@@ -68,10 +68,14 @@ class Mamba1ScanFn(torch.autograd.Function):
         flat = tensors[G:]
         n = len(_W1)
         weights = [ops.Mamba1Weights(*[_det(v) for v in flat[g * n:(g + 1) * n]]) for g in range(G)]
-        out, u, x_dbl = ops.mamba1_scan_raw(xz, weights, plan)
+        B, _, D2 = xz[0].shape
+        # recurrence checkpoints written by the forward: the reverse-scan kernel then skips its own forward sweep
+        states = torch.empty(ops.mamba1_state_shape(G, B, plan, D2 // 2, weights[0].A.shape[1]), dtype=torch.float32,
+                             device=xz[0].device)
+        out, u, x_dbl = ops.mamba1_scan_raw(xz, weights, plan, chunk_states=states)
         ctx.plan, ctx.G = plan, G
         ctx.none_mask = [t is None for t in flat]
-        ctx.save_for_backward(*xz, *[t for t in flat if t is not None], u, x_dbl)
+        ctx.save_for_backward(*xz, *[t for t in flat if t is not None], u, x_dbl, states)
         return out
 
     @staticmethod
@@ -79,7 +83,7 @@ class Mamba1ScanFn(torch.autograd.Function):
         plan, G = ctx.plan, ctx.G
         saved = list(ctx.saved_tensors)
         xz = saved[:G]
-        x_dbl, u = saved.pop(), saved.pop()
+        ws, x_dbl, u = saved.pop(), saved.pop(), saved.pop()
         it = iter(saved[G:])
         flat = [None if m else next(it) for m in ctx.none_mask]
         n = len(_W1)
@@ -95,8 +99,6 @@ class Mamba1ScanFn(torch.autograd.Function):
         dout = dout.to(x0.dtype).contiguous()
         a, _ = ops.mamba1_args(xz, weights, plan, bufs=(dout, u, x_dbl))
         f32 = dict(dtype=torch.float32, device=dev)
-        ct = int(_cabi.lib().dm_mamba1_bwd_chunk_tokens())
-        nch = (L + ct - 1) // ct
         d_xz_scan = torch.empty((G, B, K, L, 2 * D), **f32)
         du = torch.empty((G, B, K, L, D), **f32)
         ddelta = torch.empty((G, B, K, L, D), **f32)
@@ -106,10 +108,10 @@ class Mamba1ScanFn(torch.autograd.Function):
         ddtb = torch.zeros((G, D), **f32)
         dcw = torch.zeros((G, D, weights[0].conv_weight.shape[1]), **f32)
         dcb = torch.zeros((G, D), **f32)
-        ws = torch.empty((G, B, K, nch, D, N), **f32)
         gr = (_cabi.Mamba1BwdGroup * G)()
         for g in range(G):
             w = weights[g]
+            gr[g].states_valid = 1                  # ws = the forward's checkpoints
             gr[g].dout = dout[g].data_ptr()
             gr[g].d_xz_scan, gr[g].du, gr[g].ddelta = d_xz_scan[g].data_ptr(), du[g].data_ptr(), ddelta[g].data_ptr()
             gr[g].d_x_dbl, gr[g].dA = d_x_dbl[g].data_ptr(), dA[g].data_ptr()

@@ -48,6 +48,7 @@ struct M1G {
     const float* dt_bias;
     const float* A;
     const float* D;
+    float* chunk_states;
 };
 
 struct M1P {
@@ -58,6 +59,7 @@ struct M1P {
     // dynamic schedule of the scan kernel (see m1_scan_kernel): workspace + segmentation, or sched == nullptr
     int* sched;
     int seg_chunks, n_segs;
+    int save_every;            // training: tokens between two saved states (dm_mamba1_bwd_chunk_tokens), else 0
     M1G g[DM_MAX_GROUPS];
 };
 
@@ -626,7 +628,7 @@ __device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <typename T, int CPL, bool kDyn>
+template <typename T, int CPL, bool kDyn, bool kSave>
 __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
 #ifdef DM_SCAN_TRACE
     unsigned trace_sm, trace_warp;
@@ -836,6 +838,25 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
         }
     };
 
+    // training: state BEFORE every save_every-th token -> chunk_states[(seq, j / save_every, channel, 0..15)] (the
+    // backward's checkpoints; it then skips its own forward sweep)
+    // (kSave is a template flag so that the inference kernels carry none of this)
+    float* const st_base = kSave
+        ? G.chunk_states + ((seq_in_group * ((L + p.save_every - 1) / max(p.save_every, 1))) * D + c0 + lane) * kN
+        : nullptr;
+    auto save_state = [&](int j) {
+        float* dst = st_base + static_cast<int64_t>(j / p.save_every) * D * kN;
+#pragma unroll
+        for (int ch = 0; ch < CPL; ++ch)
+#pragma unroll
+            for (int n = 0; n < kN / 2; n += 2) {
+                float a0, a1, a2, a3;
+                unpack2(h[ch][n], a0, a1);
+                unpack2(h[ch][n + 1], a2, a3);
+                *reinterpret_cast<float4*>(dst + ch * 32 * kN + 2 * n) = make_float4(a0, a1, a2, a3);
+            }
+    };
+
     prefetch(c_begin);
     if constexpr (kDyn) {
         if (seg > 0) {                               // state left by the item that ran the previous segment of this unit
@@ -913,7 +934,12 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
 #pragma unroll
                 for (int ch = 0; ch < CPL; ++ch) dtv[jj][ch] = softplus_scaled(fmaf(S.ds[jj][ch * 32 + lane], kLog2e, dtb[ch]));
 #pragma unroll
-            for (int jj = 0; jj < kCH; ++jj) token(buf, jj, dtv[jj]);
+            for (int jj = 0; jj < kCH; ++jj) {
+                if constexpr (kSave) {
+                    if ((jj % 4) == 0 && ((j0 + jj) % p.save_every) == 0) save_state(j0 + jj);
+                }
+                token(buf, jj, dtv[jj]);
+            }
         } else {
             const int nrows = L - j0;
 #pragma unroll 1
@@ -921,6 +947,9 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
                 float dtv[CPL];
 #pragma unroll
                 for (int ch = 0; ch < CPL; ++ch) dtv[ch] = softplus_scaled(fmaf(S.ds[jj][ch * 32 + lane], kLog2e, dtb[ch]));
+                if constexpr (kSave) {
+                    if (((j0 + jj) % p.save_every) == 0) save_state(j0 + jj);
+                }
                 token(buf, jj, dtv);
             }
         }
@@ -1005,15 +1034,21 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
             int dev = 0;
             DM_CUDA_TRY(cudaGetDevice(&dev));
             DM_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(ScanSmem<T, 2>))));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(ScanSmem<T, 2>))));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(ScanSmem<T, 1>))));
-            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(ScanSmem<T, 2>))));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(ScanSmem<T, 1>))));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
         // two channels per lane (fewer shared-memory reads per MUFU op, 168 registers) when that still leaves >= 8
         // warps per SM; otherwise one channel per lane doubles the number of warp-units (small batches, config C5)
@@ -1027,7 +1062,17 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
             e = getenv("DM_SCAN_SEG");                   // chunks (of 8 tokens) per work item of the dynamic schedule
             force_seg = e ? atoi(e) : 0;
         }
-        if (force_cpl == 2 || (force_cpl == 0 && units2 >= 8 * n_sm)) {
+        const bool save = p.save_every > 0;       // training forward: checkpoints for the backward, static schedule
+        if (save) {
+            for (int g = 0; g < p.n_groups; ++g)
+                if (p.g[g].chunk_states == nullptr) return DM_ERR_INVALID_ARG;      // all groups or none
+            if (force_cpl == 2 || (force_cpl == 0 && units2 >= 8 * n_sm)) {
+                m1_scan_kernel<T, 2, false, true><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
+            } else {
+                const int units1 = n_seq * (p.D / 32);
+                m1_scan_kernel<T, 1, false, true><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
+            }
+        } else if (force_cpl == 2 || (force_cpl == 0 && units2 >= 8 * n_sm)) {
             const int n_chunks = (p.L + kCH - 1) / kCH;
             const int slots = 12 * n_sm;                                      // resident warps (168 registers)
             const bool have_ws = p.sched != nullptr && sched_bytes >= sched_state_offset(units2) + static_cast<size_t>(units2) * 4096;
@@ -1048,13 +1093,13 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
                 q.n_segs = (n_chunks + q.seg_chunks - 1) / q.seg_chunks;
                 const long long items = static_cast<long long>(units2) * q.n_segs;
                 const int grid = items < slots ? static_cast<int>(items) : slots;
-                m1_scan_kernel<T, 2, true><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
+                m1_scan_kernel<T, 2, true, false><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
             } else {
-                m1_scan_kernel<T, 2, false><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
+                m1_scan_kernel<T, 2, false, false><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
             }
         } else {
             const int units1 = n_seq * (p.D / 32);
-            m1_scan_kernel<T, 1, false><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
+            m1_scan_kernel<T, 1, false, false><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
         }
         DM_CUDA_TRY(cudaGetLastError());
     }
@@ -1063,6 +1108,8 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
 
 }  // namespace
 }  // namespace dm
+
+extern "C" int dm_mamba1_bwd_chunk_tokens(void);
 
 static int m1_dispatch(const dm_mamba1_args* a, int phases, void* stream) {
     using namespace dm;
@@ -1094,6 +1141,8 @@ static int m1_dispatch(const dm_mamba1_args* a, int phases, void* stream) {
         d.u = s.u; d.x_dbl = s.x_dbl;
         d.conv_w = s.conv_weight; d.conv_b = s.conv_bias; d.wx = s.x_proj_weight; d.wdt = s.dt_proj_weight;
         d.dt_bias = s.dt_bias; d.A = s.A; d.D = s.D;
+        d.chunk_states = s.chunk_states;
+        if (s.chunk_states != nullptr) p.save_every = dm_mamba1_bwd_chunk_tokens();
     }
     if (a->sched_workspace != nullptr && !aligned16(a->sched_workspace)) return DM_ERR_INVALID_ARG;
     p.sched = static_cast<int*>(a->sched_workspace);

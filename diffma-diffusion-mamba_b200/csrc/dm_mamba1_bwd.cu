@@ -34,6 +34,7 @@ struct B1G {
     const void* wdt; const float* dt_bias; const float* A; const float* D;
     float* d_xz_scan; float* du; float* ddelta; float* d_x_dbl; float* dA; float* dD; float* d_dt_bias; float* hb;
     const float* conv_w; const float* conv_b; float* d_conv_w; float* d_conv_b; const float* du_total;
+    int states_valid;
 };
 struct B1P {
     int B, K, L, D, out_order, n_groups;
@@ -201,8 +202,9 @@ __global__ void __launch_bounds__(32, DM_BWD_MINB) m1_scan_bwd_kernel(const __gr
     float h[kN];
 #pragma unroll
     for (int n = 0; n < kN; ++n) h[n] = 0.f;
-    if (n_chunks > 1) issue(0, 0, false);
-    for (int ci = 0; ci < n_chunks; ++ci) {
+    // (skipped when the training forward already stored the checkpoints: G.states_valid)
+    if (n_chunks > 1 && !G.states_valid) issue(0, 0, false);
+    for (int ci = 0; ci < n_chunks && !G.states_valid; ++ci) {
         float* hbc = hb + static_cast<int64_t>(ci) * D * kN;
 #pragma unroll
         for (int n = 0; n < kN; n += 4) *reinterpret_cast<float4*>(hbc + n) = make_float4(h[n], h[n + 1], h[n + 2], h[n + 3]);
@@ -388,7 +390,7 @@ extern "C" int dm_mamba1_scan_bwd(const dm_mamba1_args* a, const dm_mamba1_bwd_g
         d.dout = r.dout; d.do_bs = s.out_batch_stride; d.do_ds = s.out_dir_stride; d.do_ts = s.out_token_stride;
         d.u = s.u; d.x_dbl = s.x_dbl; d.wdt = s.dt_proj_weight; d.dt_bias = s.dt_bias; d.A = s.A; d.D = s.D;
         d.d_xz_scan = r.d_xz_scan; d.du = r.du; d.ddelta = r.ddelta; d.d_x_dbl = r.d_x_dbl; d.dA = r.dA; d.dD = r.dD;
-        d.d_dt_bias = r.d_dt_bias; d.hb = r.state_workspace;
+        d.d_dt_bias = r.d_dt_bias; d.hb = r.state_workspace; d.states_valid = r.states_valid != 0;
         d.conv_w = s.conv_weight; d.conv_b = s.conv_bias; d.d_conv_w = r.d_conv_weight; d.d_conv_b = r.d_conv_bias;
         d.du_total = r.du;
         if (phase == 1 && (!r.dout || !r.du || !r.ddelta || !r.d_x_dbl || !r.dA || !r.state_workspace)) return DM_ERR_INVALID_ARG;

@@ -189,7 +189,8 @@ def _sched_workspace(device, batch: int, n_dir: int, d_inner: int, groups: int):
     return ws
 
 
-def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, bufs=None, dynamic=None):
+def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, bufs=None, dynamic=None,
+                chunk_states=None):
     """Fill a ``dm_mamba1_args`` for the given groups.  Returns (args, (out, u, x_dbl)); the tensors own the memory
     the struct points at and must outlive the launch.  ``bufs`` = existing (out-shaped, u, x_dbl) tensors to point at
     instead of allocating (the backward passes dout / the saved intermediates)."""
@@ -238,16 +239,24 @@ def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: Scan
         gs.dt_bias = _ptr(_chk(w.dt_bias, torch.float32, (D,), "dt_bias"))
         gs.A = _chk(w.A, torch.float32, (D, N), "A").data_ptr()
         gs.D = _ptr(_chk(w.D, torch.float32, (D,), "D"))
+        if chunk_states is not None:            # training: recurrence checkpoints for the backward (fp32, contiguous)
+            gs.chunk_states = _chk(chunk_states[g], torch.float32, chunk_states.shape[1:], "chunk_states").data_ptr()
     return a, (out_all, u_all, xd_all)
 
 
-def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan):
+def mamba1_state_shape(G: int, B: int, plan: ScanPlan, D: int, N: int):
+    """Shape of the recurrence checkpoints the training forward hands to the backward (include/diffma_b200.h)."""
+    ct = int(_cabi.lib().dm_mamba1_bwd_chunk_tokens())
+    return (G, B, plan.n_dir, (plan.seqlen + ct - 1) // ct, D, N)
+
+
+def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, chunk_states=None):
     """One C-ABI call: conv1d+SiLU -> x_proj -> dt_proj -> softplus -> scan -> D skip -> SiLU(z) gate.
 
     xz[g]: (B, L_src, 2D) tokens-major (last-dim stride 1).  Returns (out, u, x_dbl), each with a leading group
     axis: ``out[g]`` has ``plan.out_shape``; u (scan order) and x_dbl are the intermediates the backward reads.
     """
-    a, bufs = mamba1_args(xz, weights, plan)
+    a, bufs = mamba1_args(xz, weights, plan, chunk_states=chunk_states)
     st = _cabi.lib().dm_mamba1_scan_fwd(C.byref(a), C.c_void_p(_stream_handle(xz[0].device)))
     _cabi.check(st, "dm_mamba1_scan_fwd")
     LAUNCH_COUNTER["kernels"] += 2

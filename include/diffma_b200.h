@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 3
+#define DM_ABI_VERSION 4
 
 typedef enum {
     DM_OK = 0,
@@ -82,6 +82,10 @@ typedef struct {
     const float* dt_bias;      /* (d_inner) fp32 or NULL  -- `delta_bias`                                 */
     const float* A;            /* (d_inner, d_state) fp32 -- already -exp(A_log)                          */
     const float* D;            /* (d_inner) fp32 or NULL                                                  */
+    /* training only, or NULL: the forward also stores the recurrence state BEFORE every c-th scanned token,
+     * c = dm_mamba1_bwd_chunk_tokens(): (B, n_dir, ceil(seqlen/c), d_inner, d_state) fp32, contiguous.  Handed to
+     * dm_mamba1_scan_bwd as `state_workspace` with `states_valid = 1` it saves the backward its forward sweep. */
+    float* chunk_states;
 } dm_mamba1_group;
 
 typedef struct {
@@ -138,6 +142,7 @@ typedef struct {
     float* state_workspace;    /* (B, n_dir, ceil(seqlen/c), d_inner, d_state) scratch, c = dm_mamba1_bwd_chunk_tokens() */
     float* d_conv_weight;      /* (d_inner, d_conv), accumulated                                                      */
     float* d_conv_bias;        /* (d_inner), accumulated, or NULL                                                     */
+    int64_t states_valid;      /* 1: state_workspace holds the forward's `chunk_states`; 0: scratch, the kernel fills it */
 } dm_mamba1_bwd_group;
 
 int dm_mamba1_scan_bwd(const dm_mamba1_args* args, const dm_mamba1_bwd_group* grads /* [n_groups] */, int phase,

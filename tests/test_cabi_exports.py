@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
 def test_struct_layouts_match_header_sizes():
     """ctypes mirrors of the argument structs: field counts / sizes as the C compiler lays them out."""
     from diffma_b200 import _cabi
-    assert ctypes.sizeof(_cabi.Mamba1Group) == 16 * 8
+    assert ctypes.sizeof(_cabi.Mamba1Group) == 17 * 8            # + chunk_states (ABI 4)
     assert ctypes.sizeof(_cabi.Mamba1Args) == 10 * 4 + 8 + 4 * ctypes.sizeof(_cabi.Mamba1Group) + 16   # + sched workspace ptr/size (ABI 3)
     assert ctypes.sizeof(_cabi.Mamba2Group) == 15 * 8
     assert ctypes.sizeof(_cabi.Mamba2Args) == 11 * 4 + 4 + 8 + 4 * ctypes.sizeof(_cabi.Mamba2Group)
@@ -50,10 +50,11 @@ def test_invalid_arguments_return_status_not_crash():
 
 
 def test_new_entry_points_reject_bad_arguments():
-    """ABI 3 additions: scheduler workspace sizing / alignment, backward chunking, fused row kernel."""
+    """ABI 3/4 additions: scheduler workspace sizing / alignment, backward chunking + checkpoints, fused row kernel."""
     from diffma_b200 import _cabi
+    assert ctypes.sizeof(_cabi.Mamba1BwdGroup) == 12 * 8
     lib = _cabi.lib()
-    assert lib.dm_version() == 3
+    assert lib.dm_version() == 4
     # workspace: 64 B header + 64 queue slots and 4 KB of state per (sequence, 64-channel) unit
     units = 2 * 16 * 3 * (1024 // 64)
     need = lib.dm_mamba1_sched_workspace_bytes(16, 3, 1024, 2)
