@@ -61,6 +61,25 @@ def scan_to_token_sum(g_scan: torch.Tensor, plan) -> torch.Tensor:
     return acc
 
 
+def scan_to_token_sum_all(g_scan: torch.Tensor, plan) -> torch.Tensor:
+    """``scan_to_token_sum`` for all groups at once: (G, B, K, L, C) -> (G, B, L_src, C).  When every direction is a
+    full permutation this is ONE gather (index (L_src * K) built once per plan: token l, direction k -> k * L +
+    inverse_k[l]) and one sum over K, instead of per-group, per-direction index_selects and adds."""
+    G, B, K, L, Cc = g_scan.shape
+    inv = plan.inverse_table()
+    if inv is None:
+        return torch.stack([scan_to_token_sum(g_scan[g], plan) for g in range(G)])
+    idx = getattr(plan, "_flat_inv", None)
+    if idx is None:
+        dev = g_scan.device
+        cols = [(torch.arange(L, device=dev) if inv[k] is None else inv[k]) + k * L for k in range(K)]
+        idx = torch.stack(cols, 1).reshape(-1)                 # (L_src * K): [l][k]
+        plan._flat_inv = idx
+    if K == 1:
+        return g_scan.view(G * B, L, Cc).index_select(1, idx).view(G, B, L, Cc)
+    return g_scan.view(G * B, K * L, Cc).index_select(1, idx).view(G, B, L, K, Cc).sum(3)
+
+
 class Mamba1ScanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, G, *tensors):
@@ -99,15 +118,15 @@ class Mamba1ScanFn(torch.autograd.Function):
         dout = dout.to(x0.dtype).contiguous()
         a, _ = ops.mamba1_args(xz, weights, plan, bufs=(dout, u, x_dbl))
         f32 = dict(dtype=torch.float32, device=dev)
+        W = weights[0].conv_weight.shape[1]
         d_xz_scan = torch.empty((G, B, K, L, 2 * D), **f32)
         du = torch.empty((G, B, K, L, D), **f32)
         ddelta = torch.empty((G, B, K, L, D), **f32)
-        d_x_dbl = torch.zeros((G, B, K, L, E), **f32)
-        dA = torch.zeros((G, D, N), **f32)
-        dD = torch.zeros((G, D), **f32)
-        ddtb = torch.zeros((G, D), **f32)
-        dcw = torch.zeros((G, D, weights[0].conv_weight.shape[1]), **f32)
-        dcb = torch.zeros((G, D), **f32)
+        # every accumulated buffer in ONE zero-filled allocation (one memset instead of six)
+        sizes = [G * B * K * L * E, G * D * N, G * D, G * D, G * D * W, G * D]
+        acc = torch.zeros(sum(sizes), **f32)
+        d_x_dbl, dA, dD, ddtb, dcw, dcb = (t.view(shape) for t, shape in zip(
+            acc.split(sizes), [(G, B, K, L, E), (G, D, N), (G, D), (G, D), (G, D, W), (G, D)]))
         gr = (_cabi.Mamba1BwdGroup * G)()
         for g in range(G):
             w = weights[g]
@@ -123,36 +142,37 @@ class Mamba1ScanFn(torch.autograd.Function):
         lib, st = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _cabi.check(lib.dm_mamba1_scan_bwd(C.byref(a), gr, 1, st), "dm_mamba1_scan_bwd(phase 1)")
         T = B * K * L
-        dWx, dWdt = [], []
-        # the four GEMM-shaped gradients through x_proj / dt_proj.  bf16 activations: fp32 operands on the TF32 tensor
-        # path (10-bit mantissa >= the bf16 the forward used); fp32 activations: exact fp32.
+        # the four GEMM-shaped gradients through x_proj / dt_proj, batched over the groups.  bf16 activations: fp32
+        # operands on the TF32 tensor path (10-bit mantissa >= the bf16 the forward used); fp32 activations: exact fp32.
         tf32_prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = x0.dtype != torch.float32
         try:
-            for g in range(G):
-                w = weights[g]
-                dd = ddelta[g].view(T, D)
-                dxd = d_x_dbl[g].view(T, E)
-                dxd[:, :R] = dd @ w.dt_proj_weight.float()                                   # d dt_low
-                halves = x_dbl[g].view(T, E)[:, :R].contiguous().view(torch.bfloat16)        # (T, 2R): [hi | lo]
-                dt_low = halves[:, :R].float() + halves[:, R:].float()
-                dWdt.append(dd.t() @ dt_low)
-                du[g].view(T, D).addmm_(dxd, w.x_proj_weight.float())                        # du += d_x_dbl . W_x
-                dWx.append(dxd.t() @ u[g].view(T, D).float())
+            Wdt = torch.stack([w.dt_proj_weight for w in weights]).float()                    # (G, D, R)
+            Wx = torch.stack([w.x_proj_weight for w in weights]).float()                      # (G, E, D)
+            dd = ddelta.view(G, T, D)
+            dxd = d_x_dbl.view(G, T, E)
+            dxd[:, :, :R] = torch.bmm(dd, Wdt)                                                # d dt_low
+            halves = x_dbl.view(G, T, E)[:, :, :R].contiguous().view(torch.bfloat16).float()  # (G, T, 2R): [hi | lo]
+            dt_low = halves[:, :, :R] + halves[:, :, R:]
+            dWdt = torch.bmm(dd.transpose(1, 2), dt_low)                                      # (G, D, R)
+            du.view(G, T, D).baddbmm_(dxd, Wx)                                                # du += d_x_dbl . W_x
+            dWx = torch.bmm(dxd.transpose(1, 2), u.view(G, T, D).float())                     # (G, E, D)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32_prev
         _cabi.check(lib.dm_mamba1_scan_bwd(C.byref(a), gr, 2, st), "dm_mamba1_scan_bwd(phase 2)")
         ops.LAUNCH_COUNTER["kernels"] += 2
-        dxz = [scan_to_token_sum(d_xz_scan[g], plan).to(x0.dtype) for g in range(G)]
+        dxz_all = scan_to_token_sum_all(d_xz_scan, plan).to(x0.dtype)                         # (G, B, L_src, 2D)
+        dWx = dWx.to(weights[0].x_proj_weight.dtype)
+        dWdt = dWdt.to(weights[0].dt_proj_weight.dtype)
         grads = []
         for g in range(G):
             w = weights[g]
             per = {"conv_weight": dcw[g], "conv_bias": dcb[g] if w.conv_bias is not None else None,
-                   "x_proj_weight": dWx[g].to(w.x_proj_weight.dtype), "dt_proj_weight": dWdt[g].to(w.dt_proj_weight.dtype),
+                   "x_proj_weight": dWx[g], "dt_proj_weight": dWdt[g],
                    "dt_bias": ddtb[g] if w.dt_bias is not None else None, "A": dA[g],
                    "D": dD[g] if w.D is not None else None}
             grads += [per[f] for f in _W1]
-        return (None, None, *dxz, *grads)
+        return (None, None, *dxz_all.unbind(0), *grads)
 
 
 def s6_backward_cuda(u, z_src, dt_raw, Bm, Cm, A_h, D_h, dtb_h, dv, plan, nheads):
