@@ -3,16 +3,18 @@
 //
 // Two kernels, one C-ABI call, all directions x all mixers ("groups") of a block in each launch:
 //
-//   m1_conv_xproj_kernel   one CTA per 32-token tile of one scanned sequence:
+//   m1_conv_xproj_persistent / m1_conv_xproj_kernel (kernel P)
 //                          gather rows by the scan order -> causal conv1d (sliding window in registers)
-//                          -> SiLU -> u (scan order, act dtype) ; x_dbl = u . W_x^T on the legacy tensor
-//                          path (mma.sync bf16, fp32 accumulate; fp32 I/O uses the 3-term bf16 split so the
-//                          result is fp32-accurate) -> x_dbl (fp32).
-//   m1_scan_kernel         one WARP per (sequence, 32 channels), lane = channel, 16 states in registers:
-//                          per 16-token chunk: cp.async-staged x_dbl/u/z tiles (double buffered),
-//                          dt_proj on mma.sync (W_dt fragments resident in registers), then the sequential
-//                          recurrence h = exp2(dt*A*log2e) h + dt*u*B ; y = <h, C> + D u ; out = y*silu(z)
-//                          written straight to its un-permuted (token-order) row.
+//                          -> SiLU -> u (scan order, act dtype) ; x_dbl = u . W_x^T on mma.sync (bf16 operands, fp32
+//                          accumulate; fp32 I/O uses the 3-term bf16 split so the result is fp32-accurate) -> x_dbl.
+//                          bf16 / d_inner 1024: persistent, one CTA per SM, W_x resident in shared memory, 16-token
+//                          tiles double buffered by cp.async; otherwise one CTA per 32-token tile.
+//   m1_scan_kernel (kernel S)  one WARP per (sequence, 32 or 64 channels), lane = 1 or 2 channels, 16 states per
+//                          channel in registers as packed fp32 pairs: per 8-token chunk cp.async-staged x_dbl / u / z
+//                          rows (double buffered), dt_proj on mma.sync (W_dt slice in shared memory), softplus, then
+//                          the sequential recurrence h = exp2(dt*A*log2e) h + dt*u*B ; y = <h, C> + D u ;
+//                          out = y*silu(z) written straight to its un-permuted (token-order) row.  Static launch or
+//                          persistent ready-queue schedule (see the kernel); optional state checkpoints for training.
 //
 // Why the x_proj cut: B_t, C_t and dt_low_t are reductions over all d_inner channels of token t, so no
 // channel-sliced CTA can start scanning a token before every channel of it is convolved.  The scan is
@@ -500,8 +502,8 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
 //
 // One WARP per (sequence, 64 channels); lane owns channels c0+lane and c0+32+lane, 2 x 16 states in registers
 // as packed fp32 pairs.  Two channels per lane halve the shared-memory (MIO) traffic for B/C per MUFU op and
-// give 32 independent ex2 per token, so ~10 resident warps per SM already saturate the MUFU pipe; at the
-// BASELINE shape (1536 warp-units) every unit is resident in a single wave on 148 SMs.
+// give 32 independent ex2 per token; at the BASELINE shape (1536 warp-units) every unit is resident in a single wave
+// on 148 SMs (12 warps per SM at 168 registers) and the XU pipe runs at 69 % (profiles/r01_ncu_m1_scan.txt).
 #ifndef DM_CPL1_MINB
 #define DM_CPL1_MINB 20
 #endif
@@ -548,7 +550,6 @@ __device__ __forceinline__ float softplus_scaled(float s) {
     const float l = lg2_approx(1.0f + ex2_approx(s));
     return 0.6931471805599453f * (s > 28.853900817779268f ? s : l);
 }
-__device__ __forceinline__ float softplus_fast(float x) { return softplus_scaled(x * kLog2e); }
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
