@@ -206,7 +206,9 @@ def test_fused_block_path_equals_module_path(dev, use_m2, dtype):
         fused = net(b["x"], b["t"], b["y"], b["y2"], b["w"]).float()
         with torch.enable_grad():                      # grad mode selects the unfused module path
             plain = net(b["x"], b["t"], b["y"], b["y2"], b["w"]).float().detach()
-    tol = dict(rtol=2e-4, atol=2e-4) if dtype == "fp32" else dict(rtol=3e-2, atol=3e-2)
+    # bf16: two roundings-apart evaluations of a 4-block model; upstream's bf16 tolerance (one run in ~10 exceeded
+    # atol 3e-2 on a single element: the Sigma v^2 atomics of the gated RMSNorm are order-dependent in the last bit)
+    tol = dict(rtol=2e-4, atol=2e-4) if dtype == "fp32" else BF16_TOL
     torch.testing.assert_close(fused, plain, **tol)
 
 
