@@ -92,6 +92,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// orders this thread's (and, through a preceding barrier, the CTA's) generic-proxy shared-memory accesses before
+// subsequent async-proxy (bulk copy / TMA) writes to the same locations
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // 1-D bulk asynchronous copy global -> shared (TMA engine, SASS UBLKCP); completes `bytes` on `bar`.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
