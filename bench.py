@@ -253,6 +253,17 @@ def kernel_roofline(args, device, peaks):
                      "note": "148 SM x 16 MUFU/clk x sm_max_mhz; the scan is instruction-bound on this pipe (DESIGN.md)"}}
 
 
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_oracle_rate(args, budget_s, threads=None):
     """images/s of the oracle (CPU restatement of the reference path, fp32, sequential scan) on a bounded sample."""
     from diffma_b200 import synth
@@ -314,7 +325,7 @@ def run_reference(args, world, rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                             "host_cpus": os.cpu_count()},
+                             "host_cpus": os.cpu_count(), "cpu_model": cpu_model_name()},
             "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "reference = the repo's CPU oracle port of the reference's selective_scan_ref/mamba_inner_ref path "
@@ -435,7 +446,8 @@ def main():
             step()
             t = min(step(), step())
             line["cpu_baseline"] = {"value": round(bs / t, 4), "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": sample + "; best of 2 after 1 warm-up", "host_cpus": os.cpu_count()}
+                                    "sample": sample + "; best of 2 after 1 warm-up", "host_cpus": os.cpu_count(),
+                                    "cpu_model": cpu_model_name()}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -27,7 +27,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--model", default="DiffMa-XL/4")
-    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (weak scaling: fixed as the GPU count grows)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: fix the GLOBAL batch (reference config: 256) and split it over the ranks")
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--mamba2", action="store_true", help="train with the Mamba-2 mixers (reference: train.py --use-mamba2)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -40,6 +42,10 @@ def main():
         # DDP the multi-GPU step is launched eagerly
         args.no_graph = True
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        args.batch = args.global_batch // world
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     device = torch.device("cuda", local)
@@ -164,7 +170,7 @@ def main():
         print(json.dumps({
             "metric": "training_images_per_s", "value": round(world * args.batch * args.steps / sec, 2), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(sec / args.steps * 1e3, 3),
-            "higher_is_better": True, "scaling": "weak", "dtype": "f32" if args.fp32 else "bf16", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "dtype": "f32" if args.fp32 else "bf16", "data": "synthetic",
             "config": {"workload": f"{args.model}{' --use-mamba2' if args.mamba2 else ''} training step (fwd+bwd+{'DDP all-reduce+' if world > 1 else ''}AdamW), "
                                    f"L={L}, per-GPU batch {args.batch}", "global_batch": world * args.batch,
                        "grad_allreduce_mib": round(nparam * 4 / 2 ** 20, 1)},
