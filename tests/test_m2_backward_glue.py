@@ -104,3 +104,39 @@ def _run_glue_case(layout, K):
         for j, name in enumerate(autograd_ops._W2):
             torch.testing.assert_close(grads[g * len(autograd_ops._W2) + j].double(), next(it), rtol=2e-4, atol=2e-4,
                                        msg=lambda m, name=name: f"{name}: {m}")
+
+
+@pytest.mark.parametrize("K,with_identity", [(3, True), (4, False), (1, False), (2, True)])
+def test_batched_direction_merge_is_the_adjoint_of_the_scan_gather(K, with_identity):
+    """autograd_ops.scan_to_token_sum_all (one gather + one sum for all groups, used by the Mamba-1 backward) equals the
+    per-group scan_to_token_sum and is the adjoint of gather_scan_order: <gather(x), g> == <x, merge(g)>."""
+    torch.manual_seed(K)
+    G, B, L, Cc = 2, 3, 12, 5
+    orders = [torch.randperm(L).tolist() for _ in range(K)]
+    if with_identity:
+        orders[0] = None
+    plan = ops.ScanPlan.build(orders, L, "concat", "cpu")
+    g_scan = torch.randn(G, B, K, L, Cc, dtype=torch.float64)
+    merged = autograd_ops.scan_to_token_sum_all(g_scan, plan)
+    assert merged.shape == (G, B, L, Cc)
+    for g in range(G):
+        torch.testing.assert_close(merged[g], autograd_ops.scan_to_token_sum(g_scan[g], plan))
+    x = torch.randn(B, L, Cc, dtype=torch.float64)
+    lhs = (autograd_ops.gather_scan_order(x, plan) * g_scan[0]).sum()
+    rhs = (x * merged[0]).sum()
+    torch.testing.assert_close(lhs, rhs)
+    # a second call reuses the cached flat index
+    torch.testing.assert_close(autograd_ops.scan_to_token_sum_all(g_scan, plan), merged)
+
+
+def test_batched_direction_merge_partial_cover_falls_back():
+    """EfficientVMamba-style plans (each direction covers a quarter of the tokens): no inverse permutation exists, the
+    batched merge must fall back to the index_add path and still be the adjoint of the gather."""
+    L = 16
+    quarters = [list(range(i, L, 4)) for i in range(4)]
+    plan = ops.ScanPlan.build(quarters, L, "disjoint", "cpu")
+    assert plan.inverse_table() is None
+    g_scan = torch.randn(2, 2, 4, L // 4, 3, dtype=torch.float64)
+    merged = autograd_ops.scan_to_token_sum_all(g_scan, plan)
+    x = torch.randn(2, L, 3, dtype=torch.float64)
+    torch.testing.assert_close((autograd_ops.gather_scan_order(x, plan) * g_scan[1]).sum(), (x * merged[1]).sum())
