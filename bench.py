@@ -56,7 +56,7 @@ def workload(args):
     return {"workload": f"{args.model} {'mamba2' if args.mamba2 else 'mamba1'} 1 denoise step (p_sample), "
                         f"{args.input_size}x{args.input_size}x4 latents (224x224 images at 28), L={L} tokens, "
                         f"per-GPU batch {args.batch}, bf16 autocast",
-            "model": args.model, "depth": _DEPTH[size], "tokens": L, "per_gpu_batch": args.batch,
+            "registry_key": args.model, "depth": _DEPTH[size], "tokens": L, "per_gpu_batch": args.batch,
             "mixer": "mamba2" if args.mamba2 else "mamba1", "respacing": "250",
             "l2_policy": "working set per step (bf16 weights + activations) exceeds the 126 MB L2; "
                          "kernel microbench flushes L2 explicitly between iterations"}
