@@ -19,4 +19,6 @@ def create_model_and_diffusion(name: str = "DiffMa-B/2", input_size: int = 28, u
     from .diffusion import create_diffusion
     from .model import DiffMa_models
     net = DiffMa_models[name](input_size=input_size, dt_rank=dt_rank, d_state=d_state, use_mamba2=use_mamba2)
-    return net, create_diffusion(respacing)
+    diffusion = create_diffusion(respacing)
+    net.t_table_rows = max(1000, int(getattr(diffusion, "original_num_steps", 1000)))   # integer-timestep embedding table
+    return net, diffusion

@@ -72,10 +72,12 @@ class Spiral_MambaBlock(nn.Module):
     # ---- inference path: 8 launches per block (reference: ~100), weights cached in the act dtype ----------
     def _fused_weights(self, act):
         m1, m2 = self.mamba1, self.mamba2
+        from . import ops
         params = [m1.in_proj.weight, m2.in_proj.weight, m1.out_proj.weight, m2.out_proj.weight,
                   self.adaLN_modulation[1].weight, self.adaLN_modulation[1].bias, self.attention_network[1].weight,
-                  self.attention_network[1].bias, self.attention_network[3].weight, self.attention_network[3].bias]
-        key = (act, params[0].device, tuple(p._version for p in params))
+                  self.attention_network[1].bias, self.attention_network[3].weight, self.attention_network[3].bias,
+                  self.norm1.weight, self.norm1.bias, self.attention_network[0].weight, self.attention_network[0].bias]
+        key = ops.weights_key(params, act, str(params[0].device))
         cache = getattr(self, "_fcache", None)
         if cache is not None and cache["key"] == key:
             return cache
@@ -103,8 +105,9 @@ class Spiral_MambaBlock(nn.Module):
     def _m2_out_weights(self, act):
         """(2, d_inner, d_model): out_proj weight with the gated-RMSNorm weight folded in (Mamba-2 mixers)."""
         m1, m2 = self.mamba1, self.mamba2
+        from . import ops
         ps = [m1.out_proj.weight, m2.out_proj.weight, m1.norm.weight, m2.norm.weight]
-        key = (act, ps[0].device, tuple(p._version for p in ps))
+        key = ops.weights_key(ps, act, str(ps[0].device))
         c = getattr(self, "_m2cache", None)
         if c is None or c[0] != key:
             w = torch.stack([(m.out_proj.weight.float() * m.norm.weight.float()[None, :]) for m in (m1, m2)])

@@ -48,9 +48,21 @@ def nvcc() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return LIB
+    """Compile + link under an exclusive file lock: N torchrun ranks of a fresh checkout must not run nvcc into the
+    same ``lib/obj/*.o`` concurrently (the first rank builds, the others wait and find a fresh library)."""
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
     cc = nvcc()
@@ -82,13 +94,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def ensure_built() -> str:
-    """Return the library path, building it if nvcc is available and it is missing or stale."""
+    """Return the library path, building it if it is missing or older than a source.  A failed rebuild RAISES even when
+    an old library exists: running a stale ``.so`` after a source edit silently is worse than stopping.  Only a box
+    without nvcc (a deployment that ships the prebuilt library) may use the existing file, with a warning."""
     if is_stale():
-        try:
-            build()
-        except RuntimeError:
-            if not os.path.exists(LIB):
-                raise
+        have_nvcc = bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
+        if not have_nvcc and os.path.exists(LIB):
+            import warnings
+            warnings.warn(f"diffma_b200: {LIB} is older than its sources and nvcc is not available; using it as is",
+                          RuntimeWarning, stacklevel=2)
+            return LIB
+        build()
     return LIB
 
 

@@ -6,6 +6,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <cstdlib>
+
 #include "../../include/diffma_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -25,6 +28,34 @@ extern thread_local int g_last_cuda_error;
             return DM_ERR_CUDA;                             \
         }                                                   \
     } while (0)
+
+// ---- one-time configuration, per DEVICE (function attributes and the SM count belong to a device context, not to a
+//      thread: a process that first runs on cuda:0 and then on cuda:1 must opt every kernel in again) ----
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool done(int dev) const { return dev >= 0 && dev < 64 && ((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
+    void set(int dev) { if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
+// current device ordinal and its SM count (cached per device)
+inline int current_device(int* dev, int* n_sm) {
+    static std::atomic<int> sms[64];
+    int d = 0;
+    DM_CUDA_TRY(cudaGetDevice(&d));
+    int n = (d >= 0 && d < 64) ? sms[d].load(std::memory_order_relaxed) : 0;
+    if (n == 0) {
+        DM_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d));
+        if (d >= 0 && d < 64) sms[d].store(n, std::memory_order_relaxed);
+    }
+    *dev = d;
+    *n_sm = n;
+    return DM_OK;
+}
+// experiment knobs from the environment: read once (thread-safe static init at the call site), e.g.
+//   static const int v = env_int("DM_X", 0);
+inline int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

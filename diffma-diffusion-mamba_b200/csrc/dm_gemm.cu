@@ -221,11 +221,9 @@ extern "C" int dm_gemm_bf16_tn(const void* A, int64_t a_group_stride, int64_t a_
     if (!aligned16(A) || !aligned16(B) || !aligned16(C)) return DM_ERR_INVALID_ARG;
     // tile configuration: wide N tiles when the output is wide (halves the re-reads of A), 2 CTAs per SM so one CTA's
     // epilogue overlaps the other's main loop.  DM_GEMM_CONFIG (0..2) overrides for experiments.
-    static int forced = -2;
-    if (forced == -2) {
-        const char* e = getenv("DM_GEMM_CONFIG");
-        forced = e ? atoi(e) : -1;
-    }
+    static const int forced = env_int("DM_GEMM_CONFIG", -1);
+    int dev = 0, n_sm = 0;
+    if (int e = current_device(&dev, &n_sm); e != DM_OK) return e;
     const int cfg = forced >= 0 ? forced : (N % 256 == 0 ? 4 : 0);
     const int bn = (cfg == 1 || cfg == 3 || cfg == 4) ? 256 : 128;
     CUtensorMap map_a, map_b;
@@ -239,11 +237,11 @@ extern "C" int dm_gemm_bf16_tn(const void* A, int64_t a_group_stride, int64_t a_
 #define DM_LAUNCH_GEMM(BN_, ST_, MB_)                                                                            \
     do {                                                                                                         \
         const size_t smem = ST_ * (BM + BN_) * BK * 2 + 1024 + 256;                                              \
-        static thread_local bool configured = false;                                                             \
-        if (!configured) {                                                                                       \
+        static PerDeviceOnce configured;                                                                         \
+        if (!configured.done(dev)) {                                                                             \
             DM_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN_, ST_, MB_>,                            \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-            configured = true;                                                                                   \
+            configured.set(dev);                                                                                 \
         }                                                                                                        \
         gemm_bf16_tcgen05_kernel<BN_, ST_, MB_><<<grid, kGemmThreads, smem, cs>>>(map_a, map_b, p);              \
     } while (0)

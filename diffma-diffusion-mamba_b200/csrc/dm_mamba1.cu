@@ -998,18 +998,18 @@ template <typename T>
 int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes) {
     const int n_seq = p.n_groups * p.B * p.K;
     const bool split = sizeof(T) == 4;
+    int dev = 0, n_sm = 0;
+    if (int e = current_device(&dev, &n_sm); e != DM_OK) return e;
     // kernel P
     if (phases & 1) {
         const size_t ld = static_cast<size_t>(p.D) + 8;
         const size_t bytes2 = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2 + static_cast<size_t>(p.K) * p.L * 4;
         if (!split && p.D == 1024 && bytes2 <= 227 * 1024) {                        // bf16, d_inner 1024: persistent kernel, W_x resident in shared memory
-            static thread_local int n_sm = 0;
-            if (n_sm == 0) {
-                int dev = 0;
-                DM_CUDA_TRY(cudaGetDevice(&dev));
-                DM_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            static PerDeviceOnce cfg;
+            if (!cfg.done(dev)) {
                 DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_persistent<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  227 * 1024));
+                cfg.set(dev);
             }
             const int n_tiles = n_seq * ((p.L + kTP2 - 1) / kTP2);
             const int grid = n_tiles < n_sm ? n_tiles : n_sm;
@@ -1018,23 +1018,17 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
             const size_t smem = static_cast<size_t>(kTP) * (p.D + 8) * 2 * (split ? 2 : 1);
             const size_t red = static_cast<size_t>(8) * kTP * kE * 4;
             const size_t bytes = smem > red ? smem : red;
-            static thread_local size_t configured = 0;
-            if (bytes > configured) {
-                DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 static_cast<int>(bytes)));
-                configured = bytes;
-            }
+            // (cheap, and the size depends on d_inner: set it on every launch rather than caching per thread)
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(bytes)));
             m1_conv_xproj_kernel<T><<<n_seq * p.tiles_per_seq, kPThreads, bytes, stream>>>(p);
         }
         DM_CUDA_TRY(cudaGetLastError());
     }
     // kernel S
     if (phases & 2) {
-        static thread_local int n_sm = 0;
-        if (n_sm == 0) {
-            int dev = 0;
-            DM_CUDA_TRY(cudaGetDevice(&dev));
-            DM_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        static PerDeviceOnce scfg;
+        if (!scfg.done(dev)) {
             DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(ScanSmem<T, 2>))));
             DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1050,19 +1044,18 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
             DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(ScanSmem<T, 1>))));
             DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            scfg.set(dev);
         }
         // two channels per lane (fewer shared-memory reads per MUFU op, 168 registers) when that still leaves >= 8
         // warps per SM; otherwise one channel per lane doubles the number of warp-units (small batches, config C5)
         const int units2 = n_seq * (p.D / 64);
-        static int force_cpl = -1, force_sched = -1, force_seg = 0;
-        if (force_cpl < 0) {
-            const char* e = getenv("DM_SCAN_CPL");
-            force_cpl = e ? atoi(e) : 0;
-            e = getenv("DM_SCAN_SCHED");                 // "static" | "dynamic" (default: dynamic when a workspace is given)
-            force_sched = e ? (e[0] == 's' ? 0 : 1) : 2;
-            e = getenv("DM_SCAN_SEG");                   // chunks (of 8 tokens) per work item of the dynamic schedule
-            force_seg = e ? atoi(e) : 0;
-        }
+        // experiment knobs, read once (thread-safe static initialisation)
+        static const int force_cpl = env_int("DM_SCAN_CPL", 0);
+        static const int force_sched = [] {              // "static" | "dynamic" (default: dynamic when a workspace is given)
+            const char* e = getenv("DM_SCAN_SCHED");
+            return e ? (e[0] == 's' ? 0 : 1) : 2;
+        }();
+        static const int force_seg = env_int("DM_SCAN_SEG", 0);   // chunks (of 8 tokens) per work item of the dynamic schedule
         const bool save = p.save_every > 0;       // training forward: checkpoints for the backward, static schedule
         if (save) {
             for (int g = 0; g < p.n_groups; ++g)

@@ -403,22 +403,24 @@ extern "C" int dm_mamba1_scan_bwd(const dm_mamba1_args* a, const dm_mamba1_bwd_g
     const int n_seq = p.n_groups * p.B * p.K;
     if (phase == 1) {
         const int n_units = n_seq * (p.D / 32);
+        int dev = 0, n_sm = 0;
+        if (int e = current_device(&dev, &n_sm); e != DM_OK) return e;
         if (a->act_dtype == DM_F32) {
             const size_t bytes = sizeof(BwdSmem<float>);
-            static thread_local bool cfg = false;
-            if (!cfg) {
+            static PerDeviceOnce cfg;
+            if (!cfg.done(dev)) {
                 DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
                 DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                cfg = true;
+                cfg.set(dev);
             }
             m1_scan_bwd_kernel<float><<<n_units, 32, bytes, st>>>(p, n_units);
         } else {
             const size_t bytes = sizeof(BwdSmem<__nv_bfloat16>);
-            static thread_local bool cfg = false;
-            if (!cfg) {
+            static PerDeviceOnce cfg;
+            if (!cfg.done(dev)) {
                 DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
                 DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_bwd_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                cfg = true;
+                cfg.set(dev);
             }
             m1_scan_bwd_kernel<__nv_bfloat16><<<n_units, 32, bytes, st>>>(p, n_units);
         }

@@ -10,7 +10,8 @@
 // registers.  Unlike Mamba-1 there is no cross-channel reduction before the recurrence (B, C, dt come
 // straight out of the in-projection), so the whole op is one launch; the decay is one scalar per
 // (head, token), so the MUFU load is ~6 per (b,d,l) instead of Mamba-1's 20 and the kernel is bound by
-// the FP32 pipe.  (The chunked "SSD" tensor-core form is the planned next step; see DESIGN.md.)
+// the FP32 pipe.  That sequential kernel (m2_ssd_kernel) serves fp32 I/O and odd head sizes; bf16 with headdim 64 --
+// every BASELINE config -- runs the chunked "SSD" tensor-core form m2_ssd_chunk_kernel (dm_mamba2_chunk.cuh).
 #include <cstdlib>
 
 #include "dm_common.cuh"
@@ -539,20 +540,18 @@ __global__ void __launch_bounds__(ssd::kThreads, 4) m2_ssd_chunk_kernel(const __
 
 template <typename T>
 int launch_m2(const M2P& p, cudaStream_t stream) {
+    int dev = 0, n_sm = 0;
+    if (int e = current_device(&dev, &n_sm); e != DM_OK) return e;
     if constexpr (sizeof(T) == 2) {
         // bf16, headdim 64: the chunked tensor-core form (DM_M2_CHUNK=0 forces the sequential kernel)
-        static int use_chunk = -1;
-        if (use_chunk < 0) {
-            const char* e = getenv("DM_M2_CHUNK");
-            use_chunk = e ? atoi(e) : 1;
-        }
+        static const int use_chunk = env_int("DM_M2_CHUNK", 1);
         if (use_chunk && p.P == ssd::P) {
-            static thread_local bool cfg = false;
-            if (!cfg) {
+            static PerDeviceOnce cfg;
+            if (!cfg.done(dev)) {
                 DM_CUDA_TRY(cudaFuncSetAttribute(m2_ssd_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  static_cast<int>(sizeof(ssd::Smem))));
                 DM_CUDA_TRY(cudaFuncSetAttribute(m2_ssd_chunk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                cfg = true;
+                cfg.set(dev);
             }
             const int units = p.n_groups * p.B * p.K * p.H;
             m2_ssd_chunk_kernel<<<units, ssd::kThreads, sizeof(ssd::Smem), stream>>>(p);
@@ -562,12 +561,12 @@ int launch_m2(const M2P& p, cudaStream_t stream) {
     }
     const int n_units = p.n_groups * p.B * p.K * (p.D / kSC);
     const size_t bytes = sizeof(SsdSmem<T>);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (!configured.done(dev)) {
         DM_CUDA_TRY(cudaFuncSetAttribute(m2_ssd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(bytes)));
         DM_CUDA_TRY(cudaFuncSetAttribute(m2_ssd_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
+        configured.set(dev);
     }
     m2_ssd_kernel<T><<<n_units, 32, bytes, stream>>>(p, n_units);
     DM_CUDA_TRY(cudaGetLastError());

@@ -1,29 +1,169 @@
-"""Data-parallel gradient averaging for the training step (the reference wraps the model
-in ``torch.nn.parallel.DistributedDataParallel``, train.py:153, and its only cross-GPU traffic is the gradient
-all-reduce fired by ``loss.backward()``, train.py:259).
+"""Data-parallel training state for the DiffMa step (SURVEY.md section 8a row a13 and the loop around it).
 
-``FlatGradSync`` keeps the same semantics -- parameters broadcast from rank 0 at construction, gradients AVERAGED over
-ranks every step -- but is built so that the step can be replayed as CUDA graphs: every ``p.grad`` is a view into ONE
-flat fp32 buffer (autograd accumulates into existing ``.grad`` tensors in place), so
+The reference wraps the model in ``torch.nn.parallel.DistributedDataParallel`` (train.py:153): parameters are broadcast
+from rank 0, and ``loss.backward()`` (train.py:259) all-reduces fp32 gradients in 25 MB buckets overlapped with the
+rest of the backward; then ``opt.step()`` (AdamW, lr 1e-4, weight decay 0: train.py:201,262) and ``update_ema``
+(train.py:34-43,264) walk ~1 900 parameter tensors one by one.
 
-    graph A: flat.zero_() ; forward ; backward        (no collective inside the capture)
-    eager  : ONE NCCL all-reduce of the flat buffer over NVLink / NVSwitch (592 MiB for DiffMa-XL), pre-scaled by 1/N
-    graph B: fused AdamW step
+``FlatTrainState`` keeps the same semantics -- broadcast at construction, gradients AVERAGED over ranks, AdamW, EMA --
+but lays the state out so that the whole step is ONE CUDA graph per rank:
 
-With ~5 000 kernel launches per DiffMa-XL/4 step the eager DDP step is host-bound (96 ms on 2 GPUs against 39 ms for
-the single-GPU graph); torch's DDP reducer hooks could not be captured on this stack (they deadlock), a plain
-all-reduce between two graph replays needs no capture at all.  The all-reduce is not overlapped with the backward:
-at NVLink-5 bus bandwidth it is ~2-3 ms of a ~40 ms step.
+* parameters, gradients, both Adam moments and the EMA copy are five flat fp32 buffers; every ``p.data`` / ``p.grad``
+  is a view into them (autograd accumulates into an existing ``.grad`` in place), offsets 256-byte aligned;
+* the gradient buffer is cut into buckets from its END (the backward produces the last blocks' gradients first).  A
+  post-accumulate hook per parameter counts a bucket down; when it is complete its all-reduce (NCCL over NVLink /
+  NVSwitch, SUM) is enqueued on a communication stream while the backward of the earlier blocks keeps running on the
+  compute stream -- inside the capture this becomes a fork in the graph, so replays overlap the same way;
+* the 1/N of the average is folded into the optimizer kernel's ``grad_scale``: no extra pass over the buffer;
+* ``dm_adamw_ema_step`` (csrc/dm_optim.cu) does AdamW + EMA in one pass after the streams join.
+
+``FlatGradSync`` (round 1: one blocking all-reduce between two graphs) is kept for comparison runs.
 """
 from __future__ import annotations
 
-from typing import Iterable
+from typing import Iterable, List, Optional
 
 import torch
 import torch.distributed as dist
 
+_ALIGN = 64                      # elements (256 B): every parameter view stays 16-byte aligned for the kernels
+
+
+class FlatTrainState:
+    def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int = 1, *, lr: float = 1e-4,
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, ema_decay: Optional[float] = 0.9999,
+                 bucket_mib: float = 48.0, broadcast: bool = True, process_group=None, overlap: bool = True):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatTrainState: no trainable parameters")
+        self.world, self.group, self.overlap = world_size, process_group, overlap
+        self.lr, self.betas, self.eps, self.weight_decay, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
+        dev = self.params[0].device
+        offs, off = [], 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise TypeError("FlatTrainState: master parameters are expected in fp32 (autocast handles the compute dtype)")
+            offs.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.offsets, self.total = offs, off
+        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.step_t = torch.zeros((), dtype=torch.float32, device=dev)        # device-side step counter (graph replays)
+        with torch.no_grad():
+            for p, o in zip(self.params, offs):
+                view = self.flat_p[o:o + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+        if broadcast and world_size > 1:
+            dist.broadcast(self.flat_p, src=0, group=process_group)           # what DDP's constructor does (train.py:153)
+        self.ema = self.flat_p.clone() if ema_decay is not None else None     # deepcopy(model) of train.py:156
+        # ---- buckets: contiguous ranges of the flat gradient buffer, built from the END -----------------------
+        want = int(bucket_mib * (1 << 20) / 4)
+        self.buckets = []                                                     # [lo, hi, n_params]
+        hi, n = off, 0
+        self.bucket_of = [0] * len(self.params)
+        for i in range(len(self.params) - 1, -1, -1):
+            n += 1
+            self.bucket_of[i] = len(self.buckets)
+            if hi - offs[i] >= want or i == 0:
+                self.buckets.append([offs[i], hi, n])
+                hi, n = offs[i], 0
+        self._pending = [b[2] for b in self.buckets]
+        self._fired = [False] * len(self.buckets)
+        self.comm_stream = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and world_size > 1) else None
+        self._hooks = []
+        if world_size > 1 and overlap:
+            for i, p in enumerate(self.params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(self.bucket_of[i])))
+
+    # ---- gradient synchronisation ---------------------------------------------------------------------------
+    def _make_hook(self, b: int):
+        def hook(_param):
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._reduce_bucket(b)
+        return hook
+
+    def _reduce_bucket(self, b: int) -> None:
+        if self._fired[b]:
+            return
+        self._fired[b] = True
+        lo, hi, _ = self.buckets[b]
+        chunk = self.flat_g[lo:hi]
+        if self.comm_stream is None:                                           # CPU (gloo) path of the tests
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        self.comm_stream.wait_stream(torch.cuda.current_stream())              # the bucket's gradients are complete
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+
+    def begin_step(self) -> None:
+        """Zero every gradient with one kernel and re-arm the buckets (do NOT call ``zero_grad(set_to_none=True)``: it
+        would detach the views)."""
+        self.flat_g.zero_()
+        self._pending = [b[2] for b in self.buckets]
+        self._fired = [False] * len(self.buckets)
+
+    def finish_backward(self) -> None:
+        """After ``loss.backward()``: reduce whatever the hooks have not (unused parameters, overlap off) and make the
+        compute stream wait for the communication stream.  Gradients hold the SUM over ranks afterwards."""
+        if self.world > 1:
+            if self.overlap:
+                for b in range(len(self.buckets)):
+                    self._reduce_bucket(b)
+            else:
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)   # one blocking collective
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def check_views(self) -> None:
+        gb, pb = self.flat_g.untyped_storage().data_ptr(), self.flat_p.untyped_storage().data_ptr()
+        for p in self.params:
+            if p.grad is None or p.grad.untyped_storage().data_ptr() != gb or p.data.untyped_storage().data_ptr() != pb:
+                raise RuntimeError("FlatTrainState: a parameter or its .grad no longer aliases the flat buffers "
+                                   "(something called zero_grad(set_to_none=True), .to(), or replaced .data / .grad)")
+
+    # ---- optimizer + EMA --------------------------------------------------------------------------------------
+    def optimizer_step(self) -> None:
+        """AdamW + EMA over the whole flat state: one ``dm_adamw_ema_step`` launch (CUDA only)."""
+        self.step_t.add_(1.0)
+        scale = 1.0 / self.world
+        b1, b2 = self.betas
+        if self.flat_p.is_cuda:
+            from . import _cabi, ops
+            st = _cabi.lib().dm_adamw_ema_step(
+                self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                None if self.ema is None else self.ema.data_ptr(), self.step_t.data_ptr(), self.total, self.lr, b1, b2,
+                self.eps, self.weight_decay, 0.0 if self.ema_decay is None else self.ema_decay, scale,
+                torch.cuda.current_stream(self.flat_p.device).cuda_stream)
+            _cabi.check(st, "dm_adamw_ema_step")
+            ops.LAUNCH_COUNTER["kernels"] += 1
+            ops.invalidate_weight_caches()      # (a graph REPLAY of this call does not run this line: see replayed())
+            return
+        raise RuntimeError("FlatTrainState.optimizer_step: diffma_b200 has no CPU path (state on "
+                           f"{self.flat_p.device}); oracle/ref_optim.py holds the reference update for tests")
+
+    @staticmethod
+    def replayed() -> None:
+        """Call after replaying a CUDA graph that contains ``optimizer_step``: the weights changed behind autograd's
+        back, so the inference-path weight caches (ops.weights_key) must be dropped before the next no-grad forward."""
+        from . import ops
+        ops.invalidate_weight_caches()
+
+    def ema_state(self, named_params) -> dict:
+        """name -> EMA tensor (views into the flat EMA buffer), for checkpoints (train.py:293-300 saves ema.state_dict())."""
+        if self.ema is None:
+            raise RuntimeError("FlatTrainState was built without an EMA copy")
+        by_id = {id(p): o for p, o in zip(self.params, self.offsets)}
+        return {n: self.ema[by_id[id(p)]:by_id[id(p)] + p.numel()].view_as(p) for n, p in named_params if id(p) in by_id}
+
 
 class FlatGradSync:
+    """Round-1 variant: every ``.grad`` a view into one flat buffer, ONE blocking all-reduce between two graphs."""
+
     def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int, broadcast: bool = True):
         self.params = [p for p in params if p.requires_grad]
         self.world = world_size

@@ -297,7 +297,7 @@ class GraphedSampler:
             self.model_kw["y2"] = self.y2_pooled
         self.clip = clip_denoised
         diffusion._tables(device)
-        diffusion.want_pred_xstart = False
+        self._epoch = ops.weights_epoch()
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side), torch.no_grad():
@@ -315,12 +315,21 @@ class GraphedSampler:
                 self._step()
 
     def _step(self):
-        out = self.diffusion.p_sample(self.model, self.x, self.t, clip_denoised=self.clip, model_kwargs=self.model_kw)
+        # pred_xstart is not needed by the sampling loop: switched off for THIS call only (the diffusion object is shared)
+        keep, self.diffusion.want_pred_xstart = self.diffusion.want_pred_xstart, False
+        try:
+            out = self.diffusion.p_sample(self.model, self.x, self.t, clip_denoised=self.clip, model_kwargs=self.model_kw)
+        finally:
+            self.diffusion.want_pred_xstart = keep
         self.x.copy_(out["sample"])
         self.t.sub_(1).clamp_(min=0)
 
     def step(self):
         if self.graph is not None:
+            from . import ops
+            if ops.weights_epoch() != self._epoch:
+                raise RuntimeError("GraphedSampler: the model's weights changed after this sampler was captured (the graph "
+                                   "holds pointers to cached act-dtype copies); build a new GraphedSampler")
             self.graph.replay()
         else:
             with torch.no_grad():

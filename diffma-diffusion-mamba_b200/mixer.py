@@ -108,8 +108,8 @@ class Mamba(_MixerBase):
     # ---- weights in the form the C-ABI wants ------------------------------------------------------
     def scan_weights(self, act_dtype) -> ops.Mamba1Weights:
         frozen = not torch.is_grad_enabled()
-        key = (act_dtype, tuple(p._version for p in (self.conv1d.weight, self.x_proj.weight, self.dt_proj.weight,
-                                                     self.dt_proj.bias, self.A_log, self.D)))
+        key = ops.weights_key([p for p in (self.conv1d.weight, self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
+                                           self.dt_proj.bias, self.A_log, self.D) if p is not None], act_dtype)
         if frozen and self._wcache.get("key") == key:
             return self._wcache["w"]
         w = ops.Mamba1Weights(
@@ -183,7 +183,8 @@ class Mamba2(_MixerBase):
 
     def scan_weights(self) -> ops.Mamba2Weights:
         frozen = not torch.is_grad_enabled()
-        key = tuple(p._version for p in (self.conv1d.weight, self.dt_bias, self.A_log, self.D))
+        key = ops.weights_key([p for p in (self.conv1d.weight, self.conv1d.bias, self.dt_bias, self.A_log, self.D)
+                               if p is not None])
         if frozen and self._wcache.get("key") == key:
             return self._wcache["w"]
         cd = self.conv1d.weight.shape[0]

@@ -159,7 +159,8 @@ class DiffMa(nn.Module):
 
     # ---- inference-only caches (keyed on parameter versions, rebuilt when weights change) ----------------
     def _cached(self, name, params, build):
-        key = (params[0].device, tuple(p._version for p in params))
+        from . import ops
+        key = ops.weights_key(params, str(params[0].device))
         slot = self.__dict__.setdefault("_icache", {})
         if name not in slot or slot[name][0] != key:
             with torch.no_grad():
@@ -187,7 +188,18 @@ class DiffMa(nn.Module):
         if t.dtype not in (torch.int64, torch.int32):
             return self.t_embedder(t)
         ps = list(self.t_embedder.parameters())
-        table = self._cached("temb", ps, lambda: self.t_embedder(torch.arange(1000, device=ps[0].device)).float())
+        rows = int(getattr(self, "t_table_rows", 1000))     # number of ORIGINAL diffusion steps (create_model_and_diffusion
+        #                                                     sets it; the reference's scripts always use 1000)
+
+        def build():
+            with torch.autocast("cuda", enabled=False):     # fp32 table whatever mode the first caller runs in
+                return self.t_embedder(torch.arange(rows, device=ps[0].device)).float()
+        table = self._cached(f"temb{rows}", ps, build)
+        # an index beyond the table would be a device-side assert far from here: clamp is wrong, so fail loudly instead
+        # when the host can see it (cheap: only for CPU-resident or tiny checks is this synchronising -- it is not done
+        # on CUDA tensors; callers with more steps set ``t_table_rows``)
+        if not t.is_cuda and int(t.max()) >= rows:
+            raise IndexError(f"timestep {int(t.max())} beyond the {rows}-row embedding table; set model.t_table_rows")
         return table.index_select(0, t.long())
 
     def _embed_patches(self, x):

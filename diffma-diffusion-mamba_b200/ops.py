@@ -159,6 +159,29 @@ def _chk(t: Optional[torch.Tensor], dtype, shape, name):
     return t
 
 
+# ---- inference weight caches ------------------------------------------------------------------------------
+# The no-grad fast path caches act-dtype copies / fused forms of the weights (blocks._fused_weights, DiffMa._cached,
+# Mamba.scan_weights).  Keys hold (epoch, data_ptr, _version) of EVERY parameter consumed: ``_version`` catches
+# ordinary in-place updates, ``data_ptr`` catches ``load_state_dict(assign=True)`` / re-flattened parameters, and the
+# epoch is for updates autograd cannot see -- a CUDA-graph replay of a captured optimizer step, or a kernel writing the
+# flat parameter buffer (ddp.FlatTrainState bumps it; loops that only REPLAY a captured step must call
+# ``invalidate_weight_caches()`` themselves before the next no-grad forward).  A captured GraphedSampler bakes in pointers
+# to the cached copies: it checks the epoch on every step and asks to be rebuilt when the weights have changed.
+_WEIGHTS_EPOCH = [0]
+
+
+def invalidate_weight_caches() -> None:
+    _WEIGHTS_EPOCH[0] += 1
+
+
+def weights_epoch() -> int:
+    return _WEIGHTS_EPOCH[0]
+
+
+def weights_key(params, *extra):
+    return (_WEIGHTS_EPOCH[0], tuple(extra), tuple((p.data_ptr(), p._version) for p in params))
+
+
 # kernels of OURS launched so far (bench.py reports it as gpu_launches; CUDA-graph replays are counted by the
 # sampler as captured launches x replays)
 LAUNCH_COUNTER = {"kernels": 0}
@@ -178,12 +201,20 @@ USE_DYNAMIC_SCHEDULE = True
 
 
 def _sched_workspace(device, batch: int, n_dir: int, d_inner: int, groups: int):
-    key = (str(device), batch, n_dir, d_inner, groups)
+    """One workspace per (device, STREAM, launch geometry): two same-shape scans running concurrently on different
+    streams (two samplers, a prefetch stream) must not share tickets and hand-over states.  Launches on one stream are
+    ordered, and a captured graph keeps using the workspace of the stream it was captured on."""
+    stream = torch.cuda.current_stream(device)
+    key = (str(device), stream.cuda_stream, batch, n_dir, d_inner, groups)
     ws = _SCHED_WS.get(key)
     if ws is None:
         need = int(_cabi.lib().dm_mamba1_sched_workspace_bytes(batch, n_dir, d_inner, groups))
         if need <= 0:
             return None
+        if torch.cuda.is_current_stream_capturing():
+            # a memset recorded into a graph would not have run before an eager launch that finds the cached buffer
+            raise RuntimeError("mamba1_scan: the ready-queue workspace for this shape must be allocated (and zeroed) "
+                               "before CUDA-graph capture: run the step once eagerly on the capture stream first")
         ws = torch.zeros(need, dtype=torch.uint8, device=device)
         _SCHED_WS[key] = ws
     return ws

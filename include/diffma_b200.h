@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 4
+#define DM_ABI_VERSION 5
 
 typedef enum {
     DM_OK = 0,
@@ -234,6 +234,19 @@ int dm_p_sample_update(const float* model_out, const float* x, const float* nois
 int dm_gemm_bf16_tn(const void* A, int64_t a_group_stride, int64_t a_row_stride, const void* B, int64_t b_group_stride,
                     int64_t b_row_stride, void* C, int64_t c_group_stride, int64_t c_row_stride, const float* row_scale,
                     int32_t groups, int32_t M, int32_t N, int32_t K, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Training-step tail as one pass over flat fp32 buffers: torch.optim.AdamW's update (reference train.py:201,262) and
+ * the EMA update `ema = decay*ema + (1-decay)*param` (reference train.py:34-43,264) for `n` contiguous parameters.
+ *   param *= 1 - lr*weight_decay ; m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; g = grad * grad_scale
+ *   param -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) ; ema (may be NULL) as above, from the UPDATED param.
+ * `step` points at a DEVICE float holding t (the number of steps including this one), so the call can be captured in
+ * a CUDA graph and replayed while the caller increments the counter on the device.  Any sub-range of the flat
+ * buffers may be passed (per gradient bucket, as soon as its all-reduce has landed).
+ * ---------------------------------------------------------------------------------------------------- */
+int dm_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, const float* step,
+                      int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float ema_decay,
+                      float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------ */
 int dm_version(void);                     /* DM_ABI_VERSION of the loaded library                        */

@@ -54,7 +54,7 @@ def test_new_entry_points_reject_bad_arguments():
     from diffma_b200 import _cabi
     assert ctypes.sizeof(_cabi.Mamba1BwdGroup) == 12 * 8
     lib = _cabi.lib()
-    assert lib.dm_version() == 4
+    assert lib.dm_version() == _cabi.DM_ABI_VERSION
     # workspace: 64 B header + 64 queue slots and 4 KB of state per (sequence, 64-channel) unit
     units = 2 * 16 * 3 * (1024 // 64)
     need = lib.dm_mamba1_sched_workspace_bytes(16, 3, 1024, 2)
@@ -72,3 +72,15 @@ def test_new_entry_points_reject_bad_arguments():
     p = ctypes.c_void_p(1 << 12)
     assert lib.dm_spiral_post_mix_pre(p, None, p, p, p, p, p, 1536, p, None, p, p, p, 1536, None, p, 1, 1, 384, 1e-5,
                                       _cabi.DM_BF16, None) == _cabi.DM_ERR_UNSUPPORTED
+
+
+def test_optimizer_entry_point_rejects_bad_arguments():
+    """ABI 5: dm_adamw_ema_step -- null / misaligned buffers and out-of-range coefficients are statuses, not crashes."""
+    from diffma_b200 import _cabi
+    lib = _cabi.lib()
+    p = ctypes.c_void_p(1 << 12)
+    args = (1e-4, 0.9, 0.999, 1e-8, 0.0, 0.9999, 1.0, None)
+    assert lib.dm_adamw_ema_step(None, p, p, p, p, p, 16, *args) == _cabi.DM_ERR_INVALID_ARG
+    assert lib.dm_adamw_ema_step(p, p, p, p, p, p, 0, *args) == _cabi.DM_ERR_INVALID_ARG
+    assert lib.dm_adamw_ema_step(ctypes.c_void_p((1 << 12) + 4), p, p, p, p, p, 16, *args) == _cabi.DM_ERR_INVALID_ARG
+    assert lib.dm_adamw_ema_step(p, p, p, p, p, p, 16, 1e-4, 1.5, 0.999, 1e-8, 0.0, 0.9999, 1.0, None) == _cabi.DM_ERR_INVALID_ARG

@@ -147,6 +147,71 @@ def test_flat_grad_sync_equals_single_process_gradient():
             torch.testing.assert_close(torch.from_numpy(a), p.grad, rtol=1e-5, atol=1e-6)
 
 
+def _flat_state_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from diffma_b200.ddp import FlatTrainState
+    from diffma_b200.diffusion import create_diffusion
+    torch.manual_seed(rank)                       # different initial weights per rank: the broadcast must fix that
+    net = _Tiny()
+    state = FlatTrainState(net.parameters(), world, bucket_mib=0.0005)      # ~130 elements per bucket: several buckets
+    assert len(state.buckets) >= 2 and state.buckets[0][1] == state.total and state.buckets[-1][0] == 0
+    d = create_diffusion("")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 4, 8, 8, generator=g)
+    noise = torch.randn(4, 4, 8, 8, generator=g)
+    y = torch.randn(4, 16, generator=g)
+    t = torch.tensor([3, 250, 600, 999])
+    sl = slice(rank * 2, rank * 2 + 2)
+    out = []
+    with torch.enable_grad():
+        for _ in range(2):                        # second pass: begin_step() really clears and re-arms the buckets
+            state.begin_step()
+            d.training_losses(net, x[sl], t[sl], dict(y=y[sl], y2=None, w=None), noise=noise[sl])["loss"].mean().backward()
+            fired_by_hooks = sum(state._fired)
+            state.finish_backward()
+            state.check_views()
+            out.append([(p.grad / world).clone().numpy() for p in net.parameters()])
+    if rank == 0:
+        q.put((out, [p.detach().clone().numpy() for p in net.parameters()], fired_by_hooks, len(state.buckets)))
+    dist.destroy_process_group()
+
+
+def test_flat_train_state_bucketed_sync_equals_single_process_gradient():
+    """diffma_b200.ddp.FlatTrainState: parameters and gradients as views into flat buffers, buckets reduced from the
+    END of the buffer by post-accumulate hooks (the overlap path; on gloo the collectives simply run in hook order).
+    SUM / world == the single-process gradient on the concatenated batch; rank 0's weights were broadcast."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29100 + os.getpid() % 200
+    procs = [ctx.Process(target=_flat_state_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out, weights, fired, n_buckets = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert fired == n_buckets                      # every bucket was launched from a hook, none left for finish_backward
+    sys.path.insert(0, ROOT)
+    from diffma_b200.diffusion import create_diffusion
+    torch.manual_seed(0)
+    net = _Tiny()
+    for w, p in zip(weights, net.parameters()):
+        torch.testing.assert_close(torch.from_numpy(w), p.detach())
+    d = create_diffusion("")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 4, 8, 8, generator=g)
+    noise = torch.randn(4, 4, 8, 8, generator=g)
+    y = torch.randn(4, 16, generator=g)
+    t = torch.tensor([3, 250, 600, 999])
+    with torch.enable_grad():
+        d.training_losses(net, x, t, dict(y=y, y2=None, w=None), noise=noise)["loss"].mean().backward()
+    for step_grads in out:
+        for a, p in zip(step_grads, net.parameters()):
+            torch.testing.assert_close(torch.from_numpy(a), p.grad, rtol=1e-5, atol=1e-6)
+
+
 def test_reference_arm_under_torchrun_prints_once():
     env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
