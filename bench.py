@@ -195,7 +195,8 @@ def kernel_roofline(args, device, peaks, batch=None, input_size=None, mamba2=Non
                                -torch.exp(torch.log(torch.arange(1, 17).float()).expand(D, 16)
                                           + 0.3 * torch.randn(D, 16, generator=g)).contiguous().to(device),
                                torch.ones(D, device=device)) for _ in range(2)]
-        a, keep = ops.mamba1_args(xz, w, plan)
+        # as the product path launches it: the in-projection's epilogue has already applied SiLU to z (z_is_gated)
+        a, keep = ops.mamba1_args(xz, w, plan, z_gated=True)
         lib, st = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         for phase, name in ((1, "m1_conv_xproj_kernel"), (2, "m1_scan_kernel")):
             for _ in range(3):
@@ -213,7 +214,8 @@ def kernel_roofline(args, device, peaks, batch=None, input_size=None, mamba2=Non
         # write y*silu(z) (D*2 B)
         bytes_per = 3 * D * 2 + 256
         dom, t = "m1_scan_kernel", res["m1_scan_kernel"]
-        exps = token_scans * D * 19           # 16 decays + softplus (2) + silu(z) (1, tanh) MUFU ops per (token, channel)
+        exps = token_scans * D * 18           # 16 decays + softplus (2) MUFU ops per (token, channel); the gate's SiLU is
+        #                                       evaluated once per SOURCE token in the in-projection's epilogue
     else:
         upstream = None
         Cin = 2 * D + 32 + 16

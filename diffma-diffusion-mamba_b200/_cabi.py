@@ -16,7 +16,7 @@ DM_MAX_GROUPS = 4
 DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
 EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba1_bwd_chunk_tokens", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
-           "dm_spiral_post_mix", "dm_spiral_post_mix_pre", "dm_gemm_bf16_tn", "dm_p_sample_update", "dm_adamw_ema_step", "dm_version", "dm_status_string", "dm_last_cuda_error",
+           "dm_spiral_post_mix", "dm_spiral_post_mix_pre", "dm_gemm_bf16_tn", "dm_gemm_bf16_tn_ex", "dm_p_sample_update", "dm_adamw_ema_step", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
 
@@ -40,6 +40,18 @@ class Mamba1Args(C.Structure):
         ("order", C.c_void_p),
         ("group", Mamba1Group * DM_MAX_GROUPS),
         ("sched_workspace", C.c_void_p), ("sched_workspace_bytes", C.c_int64),
+        ("z_is_gated", C.c_int32), ("reserved_", C.c_int32),
+    ]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("a_group_stride", C.c_int64), ("a_row_stride", C.c_int64), ("a_sum_stride", C.c_int64),
+        ("n_sum", C.c_int32), ("reserved_", C.c_int32),
+        ("B", C.c_void_p), ("b_group_stride", C.c_int64), ("b_row_stride", C.c_int64),
+        ("C", C.c_void_p), ("c_group_stride", C.c_int64), ("c_row_stride", C.c_int64),
+        ("row_scale", C.c_void_p), ("bias", C.c_void_p),
+        ("silu_from", C.c_int32), ("groups", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
     ]
 
 
@@ -115,6 +127,8 @@ def lib() -> C.CDLL:
                                          i32, vp]
     L.dm_gemm_bf16_tn.restype = C.c_int
     L.dm_gemm_bf16_tn.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i32, vp]
+    L.dm_gemm_bf16_tn_ex.restype = C.c_int
+    L.dm_gemm_bf16_tn_ex.argtypes = [C.POINTER(GemmArgs), vp]
     L.dm_p_sample_update.restype = C.c_int
     L.dm_p_sample_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.dm_adamw_ema_step.restype = C.c_int

@@ -16,10 +16,11 @@ from torch import nn
 from .mixer import Mamba, Mamba2, mix_groups
 
 
-# DIFFMA_GEMM=tcgen05 routes the in/out projections of the fused block path through the hand-written tcgen05 GEMM
-# (dm_gemm_bf16_tn).  Default is the library GEMM: at these shapes cuBLAS' 256x192 2-CTA tiles move ~1.5x fewer
-# bytes from L2 than our 128x256 single-CTA tiles (14-15 us vs 20 us per projection, profiles/r01_notes.md).
-_USE_TCGEN05_GEMM = os.environ.get("DIFFMA_GEMM", "cublas") == "tcgen05"
+# The dense projections of the fused (inference) block path run on the hand-written tcgen05 GEMM (dm_gemm_bf16_tn_ex):
+# in-projection with the SiLU(z) gate in its epilogue, out-projection with the CrossMerge direction sum as its A
+# producer (K = d_inner instead of 3 * d_inner), attention_network[1] with its bias in the epilogue.
+# DIFFMA_GEMM=cublas switches back to the library GEMMs (A/B comparisons, profiles/r02_notes.md).
+_USE_TCGEN05_GEMM = os.environ.get("DIFFMA_GEMM", "tcgen05") != "cublas"
 
 
 def modulate(x, shift, scale):
@@ -88,7 +89,8 @@ class Spiral_MambaBlock(nn.Module):
             "w_out": torch.stack([m1.out_proj.weight.repeat(1, K), m2.out_proj.weight.repeat(1, K)]).to(act)
                           .transpose(1, 2).contiguous(),
             "w_in_nk": torch.stack([m1.in_proj.weight, m2.in_proj.weight]).to(act).contiguous(),          # (2, N, K)
-            "w_out_nk": torch.stack([m1.out_proj.weight.repeat(1, K), m2.out_proj.weight.repeat(1, K)]).to(act).contiguous(),
+            "w_out_nk": torch.stack([m1.out_proj.weight, m2.out_proj.weight]).to(act).contiguous(),       # (2, N, d_inner)
+            "att_b32": self.attention_network[1].bias.detach().float().reshape(1, -1).contiguous(),
             "ada_w": self.adaLN_modulation[1].weight.to(act).contiguous(),
             "ada_b": self.adaLN_modulation[1].bias.to(act).contiguous(),
             "att_w": self.attention_network[1].weight.to(act).contiguous(),
@@ -102,8 +104,8 @@ class Spiral_MambaBlock(nn.Module):
         self._fcache = cache
         return cache
 
-    def _m2_out_weights(self, act):
-        """(2, d_inner, d_model): out_proj weight with the gated-RMSNorm weight folded in (Mamba-2 mixers)."""
+    def _m2_out_weights(self, act, nk=False):
+        """(2, d_inner, d_model) [nk: (2, d_model, d_inner)]: out_proj weight with the gated-RMSNorm weight folded in."""
         m1, m2 = self.mamba1, self.mamba2
         from . import ops
         ps = [m1.out_proj.weight, m2.out_proj.weight, m1.norm.weight, m2.norm.weight]
@@ -111,9 +113,9 @@ class Spiral_MambaBlock(nn.Module):
         c = getattr(self, "_m2cache", None)
         if c is None or c[0] != key:
             w = torch.stack([(m.out_proj.weight.float() * m.norm.weight.float()[None, :]) for m in (m1, m2)])
-            c = (key, w.to(act).transpose(1, 2).contiguous())
+            c = (key, w.to(act).transpose(1, 2).contiguous(), w.to(act).contiguous())
             self._m2cache = c
-        return c[1]
+        return c[2] if nk else c[1]
 
     def _forward_fused(self, x, c, w, skip=None, mod=None):
         from . import ops
@@ -141,14 +143,27 @@ class Spiral_MambaBlock(nn.Module):
         is_m2 = isinstance(m1, Mamba2)
         D = x2.shape[-1]
         with torch.autocast("cuda", enabled=False):
-            tc = act == torch.bfloat16 and _USE_TCGEN05_GEMM       # hand-written tcgen05 GEMM (dm_gemm_bf16_tn)
-            proj = ops.gemm_bf16_tn(x2, W["w_in_nk"]) if tc else torch.bmm(x2, W["w_in"])     # (2, B*L, d_in_proj)
+            tc = act == torch.bfloat16 and _USE_TCGEN05_GEMM       # hand-written tcgen05 GEMM (dm_gemm_bf16_tn_ex)
+            gated = tc and not is_m2                               # Mamba-1: the in-projection's epilogue emits silu(z)
+            if tc:
+                proj = ops.gemm_bf16_tn(x2, W["w_in_nk"], silu_from=m1.d_inner if gated else None)   # (2, B*L, d_in_proj)
+            else:
+                proj = torch.bmm(x2, W["w_in"])
             plan = m1.plan("spiral", L, x2.device)
             xs = [proj[0].view(B, L, -1), proj[1].view(B, L, -1)]
             if not is_m2:
-                y = ops.mamba1_scan(xs, [m1.scan_weights(act), m2.scan_weights(act)], plan)      # (2, B, L, K, d_inner)
-                yv = y.view(2, B * L, -1)
-                ab = ops.gemm_bf16_tn(yv, W["w_out_nk"]) if tc else torch.bmm(yv, W["w_out"])  # (2, B*L, D)
+                y = ops.mamba1_scan(xs, [m1.scan_weights(act), m2.scan_weights(act)], plan, z_gated=gated)   # (2, B, L, K, d_inner)
+                if tc:      # merge of the K directions in the GEMM's A producer: contraction over d_inner, not K * d_inner
+                    ab = ops.gemm_bf16_tn(y.view(2, B * L, plan.n_dir, -1), W["w_out_nk"])      # (2, B*L, D)
+                else:
+                    ab = torch.bmm(y.view(2, B * L, -1), W["w_out"])
+            elif tc:
+                v, ss = ops.mamba2_ssd(xs, [m1.scan_weights(), m2.scan_weights()], plan, m1.d_inner, m1.d_state,
+                                       m1.nheads, gate=True, want_sumsq=True)                     # (2,B,L,K,d), (2,B,K,L)
+                K = plan.n_dir
+                rstd = torch.rsqrt(ss / m1.d_inner + m1.norm.eps).transpose(2, 3).reshape(2, B * L * K).contiguous()
+                o = ops.gemm_bf16_tn(v.view(2, B * L * K, -1), self._m2_out_weights(act, nk=True), row_scale=rstd)
+                ab = o.view(2, B * L, K, D).sum(2)
             else:
                 v, ss = ops.mamba2_ssd(xs, [m1.scan_weights(), m2.scan_weights()], plan, m1.d_inner, m1.d_state,
                                        m1.nheads, gate=True, want_sumsq=True)                     # (2,B,L,K,d), (2,B,K,L)
@@ -160,7 +175,10 @@ class Spiral_MambaBlock(nn.Module):
                 rstd = torch.rsqrt(ss / m1.d_inner + m1.norm.eps).transpose(2, 3)                # (2, B, L, K)
                 ab = (o.view(2, B * L, K, D) * rstd.reshape(2, B * L, K, 1).to(act)).sum(2)
             lnab = ops.spiral_post_ln(ab, W["ln2"][0], W["ln2"][1])                              # (B*L, 2D)
-            hidden = F.linear(lnab, W["att_w"], W["att_b"])                                      # (B*L, D)
+            if tc:
+                hidden = ops.gemm_bf16_tn(lnab.unsqueeze(0), W["att_w"].unsqueeze(0), bias=W["att_b32"])[0]
+            else:
+                hidden = F.linear(lnab, W["att_w"], W["att_b"])                                  # (B*L, D)
             return ab, hidden
 
     def initialize_weights(self):

@@ -62,6 +62,7 @@ struct M1P {
     int* sched;
     int seg_chunks, n_segs;
     int save_every;            // training: tokens between two saved states (dm_mamba1_bwd_chunk_tokens), else 0
+    int z_gated;               // the z half of xz already holds silu(z) (in-projection epilogue): multiply, no SiLU
     M1G g[DM_MAX_GROUPS];
 };
 
@@ -629,7 +630,8 @@ __device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <typename T, int CPL, bool kDyn, bool kSave>
+// kGated: z already holds silu(z) (dm_mamba1_args.z_is_gated) -- 18 instead of 19 MUFU per (token, channel)
+template <typename T, int CPL, bool kDyn, bool kSave, bool kGated = false>
 __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
 #ifdef DM_SCAN_TRACE
     unsigned trace_sm, trace_warp;
@@ -819,12 +821,16 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
             unpack2(ysum[1], b0, b1);
             const uint64_t u2 = pack2(uu_[0], uu_[1]), z2 = pack2(zz_[0], zz_[1]);
             const uint64_t y2 = fma2(pack2(Dc[0], Dc[1]), u2, pack2(a0 + a1, b0 + b1));
-            const uint64_t half2 = pack2(0.5f, 0.5f);
-            float hz0, hz1;
-            unpack2(mul2(z2, half2), hz0, hz1);
-            const uint64_t sg = fma2(pack2(tanh_approx(hz0), tanh_approx(hz1)), half2, half2);
             float o0, o1;
-            unpack2(mul2(mul2(y2, z2), sg), o0, o1);
+            if constexpr (kGated) {
+                unpack2(mul2(y2, z2), o0, o1);
+            } else {
+                const uint64_t half2 = pack2(0.5f, 0.5f);
+                float hz0, hz1;
+                unpack2(mul2(z2, half2), hz0, hz1);
+                const uint64_t sg = fma2(pack2(tanh_approx(hz0), tanh_approx(hz1)), half2, half2);
+                unpack2(mul2(mul2(y2, z2), sg), o0, o1);
+            }
             *reinterpret_cast<T*>(out_lane + row_off) = from_f32<T>(o0);
             *reinterpret_cast<T*>(out_lane + row_off + 32 * static_cast<int>(sizeof(T))) = from_f32<T>(o1);
         } else {
@@ -833,7 +839,7 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
                 float ya, yb;
                 unpack2(ysum[ch], ya, yb);
                 const float y = fmaf(Dc[ch], uu_[ch], ya + yb);
-                const float o = y * (kSplit ? silu_fast(zz_[ch]) : silu_tanh(zz_[ch]));   // bf16 output: 1 MUFU (tanh) is enough
+                const float o = y * (kGated ? zz_[ch] : (kSplit ? silu_fast(zz_[ch]) : silu_tanh(zz_[ch])));   // bf16 output: 1 MUFU (tanh) is enough
                 *reinterpret_cast<T*>(out_lane + row_off + ch * 32 * static_cast<int>(sizeof(T))) = from_f32<T>(o);
             }
         }
@@ -1044,6 +1050,15 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
             DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(ScanSmem<T, 1>))));
             DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(ScanSmem<T, 2>))));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(ScanSmem<T, 2>))));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(ScanSmem<T, 1>))));
+            DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             scfg.set(dev);
         }
         // two channels per lane (fewer shared-memory reads per MUFU op, 168 registers) when that still leaves >= 8
@@ -1057,6 +1072,8 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
         }();
         static const int force_seg = env_int("DM_SCAN_SEG", 0);   // chunks (of 8 tokens) per work item of the dynamic schedule
         const bool save = p.save_every > 0;       // training forward: checkpoints for the backward, static schedule
+        const bool gated = p.z_gated != 0;
+        if (save && gated) return DM_ERR_INVALID_ARG;                  // the backward needs the raw z
         if (save) {
             for (int g = 0; g < p.n_groups; ++g)
                 if (p.g[g].chunk_states == nullptr) return DM_ERR_INVALID_ARG;      // all groups or none
@@ -1087,13 +1104,17 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
                 q.n_segs = (n_chunks + q.seg_chunks - 1) / q.seg_chunks;
                 const long long items = static_cast<long long>(units2) * q.n_segs;
                 const int grid = items < slots ? static_cast<int>(items) : slots;
-                m1_scan_kernel<T, 2, true, false><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
+                if (gated) m1_scan_kernel<T, 2, true, false, true><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
+                else m1_scan_kernel<T, 2, true, false><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
+            } else if (gated) {
+                m1_scan_kernel<T, 2, false, false, true><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
             } else {
                 m1_scan_kernel<T, 2, false, false><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
             }
         } else {
             const int units1 = n_seq * (p.D / 32);
-            m1_scan_kernel<T, 1, false, false><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
+            if (gated) m1_scan_kernel<T, 1, false, false, true><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
+            else m1_scan_kernel<T, 1, false, false><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
         }
         DM_CUDA_TRY(cudaGetLastError());
     }
@@ -1118,6 +1139,7 @@ static int m1_dispatch(const dm_mamba1_args* a, int phases, void* stream) {
     M1P p{};
     p.B = a->batch; p.K = a->n_dir; p.L = a->seqlen; p.D = a->d_inner;
     p.out_order = a->out_order; p.n_groups = a->n_groups;
+    p.z_gated = a->z_is_gated;
     p.tiles_per_seq = (a->seqlen + kTP - 1) / kTP;
     p.order = a->order;
     for (int g = 0; g < a->n_groups; ++g) {

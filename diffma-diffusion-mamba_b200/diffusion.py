@@ -310,8 +310,10 @@ class GraphedSampler:
         torch.cuda.synchronize(device)
         self.graph = None
         if use_graph:
+            # captured on the SAME side stream the warm-up ran on: per-stream scratch (the scan's ready-queue workspace,
+            # ops._sched_workspace) was allocated and zeroed there by the eager warm-up steps
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph), torch.no_grad():
+            with torch.cuda.graph(self.graph, stream=side), torch.no_grad():
                 self._step()
 
     def _step(self):

@@ -221,7 +221,7 @@ def _sched_workspace(device, batch: int, n_dir: int, d_inner: int, groups: int):
 
 
 def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, bufs=None, dynamic=None,
-                chunk_states=None):
+                chunk_states=None, z_gated: bool = False):
     """Fill a ``dm_mamba1_args`` for the given groups.  Returns (args, (out, u, x_dbl)); the tensors own the memory
     the struct points at and must outlive the launch.  ``bufs`` = existing (out-shaped, u, x_dbl) tensors to point at
     instead of allocating (the backward passes dout / the saved intermediates)."""
@@ -240,6 +240,7 @@ def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: Scan
     a.d_inner, a.d_state, a.dt_rank, a.d_conv = D, N, R, weights[0].conv_weight.shape[1]
     a.act_dtype, a.out_order, a.n_groups = _dtype_code(x0), plan.out_order, G
     a.order = _ptr(plan.table)
+    a.z_is_gated = int(bool(z_gated))
     if USE_DYNAMIC_SCHEDULE if dynamic is None else dynamic:
         ws = _sched_workspace(x0.device, B, plan.n_dir, D, G)
         if ws is not None:
@@ -281,25 +282,29 @@ def mamba1_state_shape(G: int, B: int, plan: ScanPlan, D: int, N: int):
     return (G, B, plan.n_dir, (plan.seqlen + ct - 1) // ct, D, N)
 
 
-def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, chunk_states=None):
+def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, chunk_states=None,
+                    z_gated: bool = False):
     """One C-ABI call: conv1d+SiLU -> x_proj -> dt_proj -> softplus -> scan -> D skip -> SiLU(z) gate.
 
     xz[g]: (B, L_src, 2D) tokens-major (last-dim stride 1).  Returns (out, u, x_dbl), each with a leading group
     axis: ``out[g]`` has ``plan.out_shape``; u (scan order) and x_dbl are the intermediates the backward reads.
     """
-    a, bufs = mamba1_args(xz, weights, plan, chunk_states=chunk_states)
+    a, bufs = mamba1_args(xz, weights, plan, chunk_states=chunk_states, z_gated=z_gated)
     st = _cabi.lib().dm_mamba1_scan_fwd(C.byref(a), C.c_void_p(_stream_handle(xz[0].device)))
     _cabi.check(st, "dm_mamba1_scan_fwd")
     LAUNCH_COUNTER["kernels"] += 2
     return bufs
 
 
-def mamba1_scan(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan) -> torch.Tensor:
-    """-> (G,) + plan.out_shape.  Forward only for now (inference / sampling); the backward op hooks in here."""
+def mamba1_scan(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, z_gated: bool = False) -> torch.Tensor:
+    """-> (G,) + plan.out_shape.  ``z_gated``: the z half of ``xz`` already holds silu(z) (inference path whose
+    in-projection epilogue applied it, ``gemm_bf16_tn(..., silu_from=d_inner)``); not differentiable."""
     if torch.is_grad_enabled() and any(t.requires_grad for t in xz):
+        if z_gated:
+            raise RuntimeError("mamba1_scan: z_gated inputs are inference-only (the backward needs the raw z)")
         from . import autograd_ops
         return autograd_ops.Mamba1ScanFn.apply(plan, len(xz), *xz, *autograd_ops.flatten_weights(weights))
-    return mamba1_scan_raw(xz, weights, plan)[0]
+    return mamba1_scan_raw(xz, weights, plan, z_gated=z_gated)[0]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -591,25 +596,41 @@ def _mod2d(mod: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # tcgen05 GEMM
 # --------------------------------------------------------------------------------------------------
-def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """C[g] = row_scale[g][:, None] * (a[g] @ b[g].T) on the hand-written tcgen05 kernel.
-    a (G, M, K), b (G, N, K) bf16 with unit stride along K; returns (G, M, N) bf16."""
+def gemm_bf16_tn(a: torch.Tensor, b: torch.Tensor, row_scale: Optional[torch.Tensor] = None,
+                 bias: Optional[torch.Tensor] = None, silu_from: Optional[int] = None) -> torch.Tensor:
+    """C[g] = silu_{cols >= silu_from}(row_scale[g][:, None] * (A[g] @ b[g].T) + bias[g]) on the hand-written tcgen05
+    kernel (``dm_gemm_bf16_tn_ex``).  b (G, N, K) bf16, K contiguous.  a is (G, M, K) -- or (G, M, S, K) with S = 3:
+    then A[g] = a[g].sum(-2) is formed in shared memory in front of the MMA (the CrossMerge direction sum as the
+    out-projection's A producer).  row_scale (G, M) fp32, bias (G, N) fp32.  Returns (G, M, N) bf16."""
     _require_cuda(a, "gemm_bf16_tn")
-    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.dim() != 3 or b.dim() != 3:
-        raise TypeError("gemm_bf16_tn: (G, M, K) x (G, N, K) bf16 operands expected")
-    G, M, K = a.shape
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.dim() not in (3, 4) or b.dim() != 3:
+        raise TypeError("gemm_bf16_tn: (G, M, [S,] K) x (G, N, K) bf16 operands expected")
+    G, M, K = a.shape[0], a.shape[1], a.shape[-1]
+    S = a.shape[2] if a.dim() == 4 else 1
     N = b.shape[1]
-    if b.shape[0] != G or b.shape[2] != K or a.stride(2) != 1 or b.stride(2) != 1:
+    if b.shape[0] != G or b.shape[2] != K or a.stride(-1) != 1 or b.stride(2) != 1:
         raise RuntimeError("gemm_bf16_tn: shape / stride mismatch")
     c = torch.empty((G, M, N), dtype=torch.bfloat16, device=a.device)
-    rs = None
+    g = _cabi.GemmArgs()
+    g.A, g.a_group_stride, g.a_row_stride = a.data_ptr(), a.stride(0), a.stride(1)
+    g.a_sum_stride, g.n_sum = (a.stride(2) if S > 1 else 0), S
+    g.B, g.b_group_stride, g.b_row_stride = b.data_ptr(), b.stride(0), b.stride(1)
+    g.C, g.c_group_stride, g.c_row_stride = c.data_ptr(), c.stride(0), c.stride(1)
+    keep = []
     if row_scale is not None:
         rs = _f32c(row_scale, "row_scale")
         assert tuple(rs.shape) == (G, M)
-    st = _cabi.lib().dm_gemm_bf16_tn(a.data_ptr(), a.stride(0), a.stride(1), b.data_ptr(), b.stride(0), b.stride(1),
-                                     c.data_ptr(), c.stride(0), c.stride(1), None if rs is None else rs.data_ptr(),
-                                     G, M, N, K, _stream_handle(a.device))
-    _cabi.check(st, "dm_gemm_bf16_tn")
+        g.row_scale = rs.data_ptr()
+        keep.append(rs)
+    if bias is not None:
+        bs = _f32c(bias, "bias")
+        assert tuple(bs.shape) == (G, N)
+        g.bias = bs.data_ptr()
+        keep.append(bs)
+    g.silu_from = N if silu_from is None else int(silu_from)
+    g.groups, g.M, g.N, g.K = G, M, N, K
+    st = _cabi.lib().dm_gemm_bf16_tn_ex(C.byref(g), C.c_void_p(_stream_handle(a.device)))
+    _cabi.check(st, "dm_gemm_bf16_tn_ex")
     LAUNCH_COUNTER["kernels"] += 1
     return c
 

@@ -107,6 +107,11 @@ typedef struct {
      * can run concurrently (different streams). */
     void* sched_workspace;
     int64_t sched_workspace_bytes;
+    /* Non-zero: the z half of `xz` already holds silu(z) (the in-projection's epilogue applied it once per source
+     * token, dm_gemm_bf16_tn_ex `silu_from`), so the scan multiplies by it instead of evaluating SiLU once per
+     * direction.  Inference only: the backward needs the raw z and rejects this flag. */
+    int32_t z_is_gated;
+    int32_t reserved_;
 } dm_mamba1_args;
 
 int dm_mamba1_scan_fwd(const dm_mamba1_args* args, void* stream);
@@ -234,6 +239,29 @@ int dm_p_sample_update(const float* model_out, const float* x, const float* nois
 int dm_gemm_bf16_tn(const void* A, int64_t a_group_stride, int64_t a_row_stride, const void* B, int64_t b_group_stride,
                     int64_t b_row_stride, void* C, int64_t c_group_stride, int64_t c_row_stride, const float* row_scale,
                     int32_t groups, int32_t M, int32_t N, int32_t K, void* stream);
+
+/* The same kernel with everything it fuses that a library GEMM cannot:
+ *   C[g] = epilogue( (A_0[g] + ... + A_{n_sum-1}[g]) . B[g]^T ),  epilogue(v) = silu_{col >= silu_from}( row_scale * v + bias )
+ *   - n_sum (1 or 3) slices of every A row, a_sum_stride elements apart, are summed in shared memory in front of the
+ *     MMA: the CrossMerge direction sum (reference block/mamba.py:60-82) as the out-projection's A producer, so the
+ *     contraction is K = d_inner instead of n_dir * d_inner and the merged tensor never exists in HBM;
+ *   - bias (groups, N) fp32 or NULL: attention_network[1]'s bias (reference block/mamba_block.py:52-53);
+ *   - silu_from (multiple of 32; >= N disables): SiLU on columns [silu_from, N): the in-projection emits silu(z) for
+ *     the gate once per source token (see dm_mamba1_args.z_is_gated). */
+typedef struct {
+    const void* A;             /* (groups, M, n_sum, K) bf16 as strides: group, row, summed slice; K contiguous      */
+    int64_t a_group_stride, a_row_stride, a_sum_stride;
+    int32_t n_sum, reserved_;
+    const void* B;             /* (groups, N, K) bf16, K contiguous                                                   */
+    int64_t b_group_stride, b_row_stride;
+    void* C;                   /* (groups, M, N) bf16, N contiguous                                                   */
+    int64_t c_group_stride, c_row_stride;
+    const float* row_scale;    /* (groups, M) fp32 or NULL                                                            */
+    const float* bias;         /* (groups, N) fp32 or NULL                                                            */
+    int32_t silu_from;
+    int32_t groups, M, N, K;
+} dm_gemm_args;
+int dm_gemm_bf16_tn_ex(const dm_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Training-step tail as one pass over flat fp32 buffers: torch.optim.AdamW's update (reference train.py:201,262) and

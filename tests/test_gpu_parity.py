@@ -230,6 +230,59 @@ def test_tcgen05_gemm_matches_fp32_reference(dev, G, M, N, K):
     assert (c2 - ref * rs[..., None]).abs().max().item() <= 6e-3 * scale
 
 
+@pytest.mark.parametrize("G,M,N,K,S", [(2, 3136, 512, 1024, 3), (1, 200, 136, 72, 3), (2, 3136, 2048, 512, 1), (1, 3136, 512, 1024, 1),
+                                       (3, 77, 264, 1024, 3), (2, 6000, 512, 1024, 3)])
+def test_tcgen05_gemm_fused_producer_and_epilogues(dev, G, M, N, K, S):
+    """dm_gemm_bf16_tn_ex: summed-A producer (S = 3 direction slices added in shared memory in front of the MMA), bias,
+    row scale and SiLU-on-a-column-range epilogues, persistent tiles (more tiles than SMs at M = 6000) -- vs fp32 math on
+    the same bf16 operands.  Tolerance: the merged A is rounded to bf16 once (2^-9 relative per element) and the output
+    once (2^-9): 6e-3 of the output scale."""
+    from diffma_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K + S)
+    a = torch.randn(G, M, S, K, generator=g).bfloat16().to(dev)
+    b = torch.randn(G, N, K, generator=g).bfloat16().to(dev)
+    bias = torch.randn(G, N, generator=g).to(dev)
+    rs = (torch.rand(G, M, generator=g) + 0.5).to(dev)
+    silu_from = (N // 64) * 32                                  # a multiple of 32 inside the matrix
+    a_in = a if S > 1 else a[:, :, 0]
+    asum = a.float().sum(2)
+    base = torch.bmm(asum, b.float().transpose(1, 2))
+    scale = base.abs().max().item()
+    c0 = ops.gemm_bf16_tn(a_in, b).float()
+    assert (c0 - base).abs().max().item() <= 6e-3 * scale
+    full = base * rs[..., None] + bias[:, None, :]
+    full[..., silu_from:] = torch.nn.functional.silu(full[..., silu_from:])
+    c1 = ops.gemm_bf16_tn(a_in, b, row_scale=rs, bias=bias, silu_from=silu_from).float()
+    assert (c1 - full).abs().max().item() <= 8e-3 * max(scale, full.abs().max().item())
+    # strided A rows (a view into a wider buffer), as the block passes them
+    wide = torch.zeros(G, M, S, K + 64, dtype=torch.bfloat16, device=dev)
+    wide[..., :K] = a
+    av = wide[..., :K]
+    c2 = ops.gemm_bf16_tn(av if S > 1 else av[:, :, 0], b).float()
+    assert torch.equal(c2, c0)
+
+
+def test_gated_scan_equals_scan_with_silu_inside(dev):
+    """dm_mamba1_args.z_is_gated: feeding silu(z) (as the in-projection epilogue writes it) with the flag set gives the
+    result of feeding z without it, up to the bf16 rounding of silu(z) -- both the 1- and the 2-channel-per-lane kernel."""
+    from diffma_b200 import ops, scan_orders
+    ml, _ = scan_orders.spiral(14)
+    for B in (2, 16):
+        xz, p = _m1_inputs(B, 196, seed=5 + B)
+        xz_t = xz.transpose(1, 2).contiguous().bfloat16().to(dev)            # (B, L, 2D)
+        w = ops.Mamba1Weights(p["conv_w"].reshape(1024, 4).to(dev), p["conv_b"].to(dev), p["x_proj"].bfloat16().to(dev),
+                              p["dt_proj"].bfloat16().to(dev), p["dt_bias"].to(dev), p["A"].to(dev), p["D"].to(dev))
+        plan = ops.ScanPlan.build([None, ml[2], ml[3]], 196, "concat", dev)
+        ref = ops.mamba1_scan([xz_t, xz_t], [w, w], plan).float()
+        gz = xz_t.clone()
+        gz[..., 1024:] = torch.nn.functional.silu(xz_t[..., 1024:].float()).bfloat16()
+        got = ops.mamba1_scan([gz, gz], [w, w], plan, z_gated=True).float()
+        torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2)
+        with pytest.raises(RuntimeError, match="inference-only"):
+            with torch.enable_grad():
+                ops.mamba1_scan([gz.requires_grad_(True)], [w], plan, z_gated=True)
+
+
 def test_tcgen05_gemm_path_in_block(dev, monkeypatch):
     """The fused block with DIFFMA_GEMM=tcgen05 (projections on dm_gemm_bf16_tn) equals the library-GEMM path."""
     from diffma_b200 import blocks, model as M, synth

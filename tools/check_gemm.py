@@ -33,4 +33,12 @@ bt = b.transpose(1, 2).contiguous(); b2t = b2.transpose(1, 2).contiguous()
 import os
 print('config', os.environ.get('DM_GEMM_CONFIG'))
 print('in_proj  ours %.1f us  cublas %.1f us' % (t(lambda: ops.gemm_bf16_tn(a, b)), t(lambda: torch.bmm(a, bt))))
-print('out_proj ours %.1f us  cublas %.1f us' % (t(lambda: ops.gemm_bf16_tn(a2, b2)), t(lambda: torch.bmm(a2, b2t))))
+# what a merged out-projection (sum of the 3 directions in the A producer => K = 1024) costs as a plain GEMM, and the
+# attention_network Linear (1024 -> 512)
+a3 = torch.randn(2, 3136, 1024, device=dev).bfloat16(); b3 = torch.randn(2, 512, 1024, device=dev).bfloat16()
+b3t = b3.transpose(1, 2).contiguous()
+a2m = torch.randn(2, 3136, 3, 1024, device=dev).bfloat16()
+print("out_proj ours K=3072 %.1f us  merged n_sum=3 %.1f us  cublas K=3072 %.1f us" % (t(lambda: ops.gemm_bf16_tn(a2, b2)), t(lambda: ops.gemm_bf16_tn(a2m, b3)), t(lambda: torch.bmm(a2, b2t))))
+print('K=1024   ours %.1f us  cublas %.1f us' % (t(lambda: ops.gemm_bf16_tn(a3, b3)), t(lambda: torch.bmm(a3, b3t))))
+a4 = torch.randn(1, 3136, 1024, device=dev).bfloat16(); b4 = torch.randn(1, 512, 1024, device=dev).bfloat16()
+print('att lin  ours %.1f us  cublas %.1f us' % (t(lambda: ops.gemm_bf16_tn(a4, b4)), t(lambda: torch.nn.functional.linear(a4[0], b4[0]))))
