@@ -16,7 +16,8 @@ DM_MAX_GROUPS = 4
 DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
 EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba1_bwd_chunk_tokens", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
-           "dm_spiral_post_mix", "dm_spiral_post_mix_pre", "dm_gemm_bf16_tn", "dm_gemm_bf16_tn_ex", "dm_p_sample_update", "dm_adamw_ema_step", "dm_version", "dm_status_string", "dm_last_cuda_error",
+           "dm_spiral_post_mix", "dm_spiral_post_mix_pre", "dm_spiral_pre_bwd", "dm_spiral_post_mix_bwd", "dm_spiral_post_ln_bwd",
+           "dm_merge_directions", "dm_gemm_bf16_tn", "dm_gemm_bf16_tn_ex", "dm_p_sample_update", "dm_adamw_ema_step", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
 
@@ -125,6 +126,14 @@ def lib() -> C.CDLL:
     L.dm_spiral_post_mix_pre.restype = C.c_int
     L.dm_spiral_post_mix_pre.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, f32,
                                          i32, vp]
+    L.dm_spiral_pre_bwd.restype = C.c_int
+    L.dm_spiral_pre_bwd.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, f32, i32, vp]
+    L.dm_spiral_post_mix_bwd.restype = C.c_int
+    L.dm_spiral_post_mix_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp]
+    L.dm_spiral_post_ln_bwd.restype = C.c_int
+    L.dm_spiral_post_ln_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]
+    L.dm_merge_directions.restype = C.c_int
+    L.dm_merge_directions.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.dm_gemm_bf16_tn.restype = C.c_int
     L.dm_gemm_bf16_tn.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i32, vp]
     L.dm_gemm_bf16_tn_ex.restype = C.c_int
@@ -132,7 +141,8 @@ def lib() -> C.CDLL:
     L.dm_p_sample_update.restype = C.c_int
     L.dm_p_sample_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     L.dm_adamw_ema_step.restype = C.c_int
-    L.dm_adamw_ema_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, vp]
+    f64 = C.c_double
+    L.dm_adamw_ema_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, f64, f64, vp]
     if L.dm_version() != DM_ABI_VERSION:
         raise RuntimeError(f"diffma_b200: library ABI {L.dm_version()} != binding ABI {DM_ABI_VERSION}; rebuild")
     _LIB = L

@@ -161,7 +161,9 @@ class Mamba1ScanFn(torch.autograd.Function):
             torch.backends.cuda.matmul.allow_tf32 = tf32_prev
         _cabi.check(lib.dm_mamba1_scan_bwd(C.byref(a), gr, 2, st), "dm_mamba1_scan_bwd(phase 2)")
         ops.LAUNCH_COUNTER["kernels"] += 2
-        dxz_all = scan_to_token_sum_all(d_xz_scan, plan).to(x0.dtype)                         # (G, B, L_src, 2D)
+        dxz_all = ops.merge_directions(d_xz_scan, plan, x0.dtype)                             # (G, B, L_src, 2D), one kernel
+        if dxz_all is None:
+            dxz_all = scan_to_token_sum_all(d_xz_scan, plan).to(x0.dtype)
         dWx = dWx.to(weights[0].x_proj_weight.dtype)
         dWdt = dWdt.to(weights[0].dt_proj_weight.dtype)
         grads = []
@@ -335,3 +337,60 @@ class Mamba2SsdFn(torch.autograd.Function):
         dzx, grads = mamba2_backward(zx, weights, plan, d_inner, d_state, nheads, v, gv,
                                      gss if ctx.want_sumsq else None)
         return (None, None, None, None, None, None, None, *dzx, *grads)
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused row kernels of the Spiral block in the training path (forward = the inference kernels of csrc/dm_block.cu,
+# backward = their adjoints in csrc/dm_block_bwd.cu)
+# ------------------------------------------------------------------------------------------------------
+class SpiralPreFn(torch.autograd.Function):
+    """x (B,L,D) fp32 [+ skip], norm1 weight / bias, mod (B, 3D) fp32, w (B*L) fp32 or None -> (2, B*L, D) act dtype:
+    [modulate(LN(x + skip)) ; the same * w]   (reference block/mamba_block.py:101-105, model.py:290-292)."""
+
+    @staticmethod
+    def forward(ctx, x, skip, ln_w, ln_b, mod, w, act_dtype):
+        x, mod = x.detach(), mod.detach()
+        lw, lb = ln_w.detach().float().contiguous(), ln_b.detach().float().contiguous()
+        sk = None if skip is None else skip.detach()
+        out2 = ops.spiral_pre(x, sk, lw, lb, mod, w, act_dtype)
+        ctx.save_for_backward(x, sk, lw, lb, mod, w)
+        ctx.has_skip = skip is not None
+        return out2
+
+    @staticmethod
+    def backward(ctx, d_out2):
+        x, sk, lw, lb, mod, w = ctx.saved_tensors
+        dx, d_mod, d_lw, d_lb = ops.spiral_pre_bwd(x, sk, lw, lb, mod, w, d_out2)
+        return dx, (dx if ctx.has_skip else None), d_lw, d_lb, d_mod, None, None
+
+
+class SpiralPostFn(torch.autograd.Function):
+    """ab (2, B*L, D) act dtype -> x_out = (x + skip) + gate * (alpha a + (1 - alpha) b), alpha = sigmoid(Linear(SiLU(
+    Linear(LN(cat(a, b))))))   (reference block/mamba_block.py:110-114): post_ln kernel, one GEMM, post_mix kernel."""
+
+    @staticmethod
+    def forward(ctx, x, skip, ab, ln2_w, ln2_b, att_w, att_b, w3, b3, mod):
+        x, ab, mod = x.detach(), ab.detach(), mod.detach()
+        sk = None if skip is None else skip.detach()
+        act = ab.dtype
+        B, L, D = x.shape
+        l2w, l2b = ln2_w.detach().float().contiguous(), ln2_b.detach().float().contiguous()
+        aw = att_w.detach().to(act).contiguous()
+        w3f, b3f = w3.detach().float().reshape(-1).contiguous(), b3.detach().float().reshape(-1).contiguous()
+        with torch.autocast("cuda", enabled=False):
+            lnab = ops.spiral_post_ln(ab, l2w, l2b)
+            hidden = torch.nn.functional.linear(lnab, aw, att_b.detach().to(act))
+            x_out = ops.spiral_post_mix(x, sk, ab, hidden, w3f, b3f, mod)
+        ctx.save_for_backward(ab, lnab, hidden, aw, l2w, w3f, b3f, mod)
+        ctx.has_skip, ctx.BL, ctx.shapes = skip is not None, (B, L), (w3.shape, b3.shape)
+        return x_out
+
+    @staticmethod
+    def backward(ctx, d_x_out):
+        ab, lnab, hidden, aw, l2w, w3f, b3f, mod = ctx.saved_tensors
+        B, L = ctx.BL
+        with torch.autocast("cuda", enabled=False):
+            d_ab, d_mod, d_l2w, d_l2b, d_aw, d_att_b, d_w3, d_b3 = ops.spiral_post_bwd(d_x_out, ab, lnab, hidden, aw, l2w, w3f,
+                                                                                     b3f, mod, B, L)
+        return (d_x_out, (d_x_out if ctx.has_skip else None), d_ab, d_l2w, d_l2b, d_aw, d_att_b, d_w3.view(ctx.shapes[0]),
+                d_b3.view(ctx.shapes[1]), d_mod)

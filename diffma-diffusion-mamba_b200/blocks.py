@@ -16,11 +16,18 @@ from torch import nn
 from .mixer import Mamba, Mamba2, mix_groups
 
 
-# The dense projections of the fused (inference) block path run on the hand-written tcgen05 GEMM (dm_gemm_bf16_tn_ex):
-# in-projection with the SiLU(z) gate in its epilogue, out-projection with the CrossMerge direction sum as its A
-# producer (K = d_inner instead of 3 * d_inner), attention_network[1] with its bias in the epilogue.
-# DIFFMA_GEMM=cublas switches back to the library GEMMs (A/B comparisons, profiles/r02_notes.md).
-_USE_TCGEN05_GEMM = os.environ.get("DIFFMA_GEMM", "tcgen05") != "cublas"
+# DIFFMA_GEMM=tcgen05 routes the dense projections of the fused (inference) block path through the hand-written tcgen05
+# GEMM (dm_gemm_bf16_tn_ex): in-projection with the SiLU(z) gate in its epilogue, out-projection with the CrossMerge
+# direction sum as its A producer (K = d_inner instead of 3 * d_inner), attention_network[1] with its bias in the
+# epilogue.  Default is the library GEMM: these projections are plain GEMMs with K <= 3072 over 3 136 rows and are bound
+# by L2 -> SM operand traffic, where cuBLAS' 256x192 two-CTA tiles move ~22 % fewer bytes per output than our
+# persistent 128x256 one-CTA tiles; measured r02 (profiles/r02_notes.md): 19.2 vs 14.2 us (in), 19.8 vs 15.5 us (out,
+# even with 3x fewer flops), 9.0 vs 5.6 us (attention Linear) -- and the scan's gain from the hoisted gate (131 -> 125 us)
+# does not pay for the difference.
+_USE_TCGEN05_GEMM = os.environ.get("DIFFMA_GEMM", "cublas") == "tcgen05"
+# DIFFMA_FUSED_TRAIN=0: differentiate the block glue op by op with torch autograd (the module path below) instead of the
+# fused row kernels + their hand-written adjoints (A/B runs and the gradient parity tests)
+_FUSED_TRAIN = os.environ.get("DIFFMA_FUSED_TRAIN", "1") != "0"
 
 
 def modulate(x, shift, scale):
@@ -61,6 +68,9 @@ class Spiral_MambaBlock(nn.Module):
         if (not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 512
                 and x.is_contiguous()):
             return self._forward_fused(x, c, w, skip)
+        if (_FUSED_TRAIN and torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 512
+                and x.is_contiguous() and (w is None or not w.requires_grad)):
+            return self._forward_train_fused(x, c, w, skip)
         if skip is not None:
             x = x + skip
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)
@@ -69,6 +79,22 @@ class Spiral_MambaBlock(nn.Module):
         a, b = mix_groups([self.mamba1, self.mamba2], [x_ssm, w_ssm], "spiral")
         alpha = self.attention_network(torch.cat([a, b], dim=-1))
         return x + gate.unsqueeze(1) * (alpha * a + (1 - alpha) * b)
+
+    # ---- training path: the same row kernels as inference with autograd Functions around them (their adjoints live in
+    #      csrc/dm_block_bwd.cu); the mixers go through mix_groups (autograd of dm_mamba1_scan_bwd) ---------------------
+    def _forward_train_fused(self, x, c, w, skip=None):
+        from .autograd_ops import SpiralPostFn, SpiralPreFn
+        from .mixer import _act_dtype
+        B, L, D = x.shape
+        act = _act_dtype(x)
+        mod = self.adaLN_modulation(c).float()                                                  # (B, 3D) = [shift | scale | gate]
+        wrow = None if w is None else w.detach().reshape(B * L).float().contiguous()
+        sk = None if skip is None else skip.contiguous()
+        x2 = SpiralPreFn.apply(x, sk, self.norm1.weight, self.norm1.bias, mod, wrow, act)      # (2, B*L, D)
+        a, b = mix_groups([self.mamba1, self.mamba2], [x2[0].view(B, L, D), x2[1].view(B, L, D)], "spiral")
+        ab = torch.stack([a.reshape(B * L, D), b.reshape(B * L, D)]).to(act)
+        an = self.attention_network
+        return SpiralPostFn.apply(x, sk, ab, an[0].weight, an[0].bias, an[1].weight, an[1].bias, an[3].weight, an[3].bias, mod)
 
     # ---- inference path: 8 launches per block (reference: ~100), weights cached in the act dtype ----------
     def _fused_weights(self, act):

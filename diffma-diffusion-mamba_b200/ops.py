@@ -652,3 +652,78 @@ def p_sample_update(model_out, x, noise, table, t, clip_denoised=False, want_pre
     _cabi.check(st, "dm_p_sample_update")
     LAUNCH_COUNTER["kernels"] += 1
     return sample, pred
+
+
+# --------------------------------------------------------------------------------------------------
+# adjoints of the row kernels (training path) and of the CrossScan gather
+# --------------------------------------------------------------------------------------------------
+def spiral_pre_bwd(x, skip, ln_weight, ln_bias, mod, w, d_out2, eps: float = 1e-5):
+    """Adjoint of ``spiral_pre``: d_out2 (2, B*L, D) -> (dx (B,L,D) fp32, d_mod (B, 3D) fp32 [gate part zero],
+    d_ln_weight (D), d_ln_bias (D))."""
+    B, L, D = x.shape
+    dx = torch.empty_like(x)
+    small = torch.zeros(B * 3 * D + 2 * D, dtype=torch.float32, device=x.device)
+    d_mod, d_lw, d_lb = small[:B * 3 * D].view(B, 3 * D), small[B * 3 * D:B * 3 * D + D], small[B * 3 * D + D:]
+    if not d_out2.is_contiguous():
+        d_out2 = d_out2.contiguous()
+    st = _cabi.lib().dm_spiral_pre_bwd(
+        _f32c(x, "x").data_ptr(), None if skip is None else _f32c(skip, "skip").data_ptr(),
+        _f32c(ln_weight, "ln_weight").data_ptr(), _f32c(ln_bias, "ln_bias").data_ptr(), _mod2d(mod).data_ptr(), mod.stride(0),
+        None if w is None else _f32c(w, "w").data_ptr(), d_out2.data_ptr(), dx.data_ptr(), d_mod.data_ptr(), 3 * D,
+        d_lw.data_ptr(), d_lb.data_ptr(), B, L, D, eps, _dtype_code(d_out2), _stream_handle(x.device))
+    _cabi.check(st, "dm_spiral_pre_bwd")
+    LAUNCH_COUNTER["kernels"] += 1
+    return dx, d_mod, d_lw, d_lb
+
+
+def spiral_post_bwd(d_x_out, ab, lnab, hidden, att_w, ln2_weight, w3, b3, mod, B: int, L: int):
+    """Adjoint of post_ln -> attention_network[1] -> post_mix.  d_x_out (B,L,D) fp32; ab (2, rows, D), lnab (rows, 2D),
+    hidden (rows, D), att_w (D, 2D) in the act dtype.  Returns (d_ab (2, rows, D) act, d_mod (B, 3D) fp32 [gate part],
+    d_ln2_weight (2D), d_ln2_bias (2D), d_att_w (D, 2D) fp32, d_att_b (D) fp32, d_w3 (D), d_b3 (1))."""
+    rows, D = hidden.shape
+    dev = d_x_out.device
+    d_ab = torch.empty_like(ab)
+    d_hidden = torch.empty_like(hidden)
+    small = torch.zeros(B * 3 * D + D + 4 + 4 * D, dtype=torch.float32, device=dev)
+    o = B * 3 * D
+    d_mod, d_w3, d_b3 = small[:o].view(B, 3 * D), small[o:o + D], small[o + D:o + D + 1]
+    d_l2w, d_l2b = small[o + D + 4:o + D + 4 + 2 * D], small[o + D + 4 + 2 * D:]
+    lib, st = _cabi.lib(), _stream_handle(dev)
+    code = _dtype_code(ab)
+    if not d_x_out.is_contiguous():
+        d_x_out = d_x_out.contiguous()
+    s = lib.dm_spiral_post_mix_bwd(_f32c(d_x_out, "d_x_out").data_ptr(), ab.data_ptr(), hidden.data_ptr(),
+                                   _f32c(w3, "w3").data_ptr(), _f32c(b3, "b3").data_ptr(), _mod2d(mod).data_ptr(),
+                                   mod.stride(0), d_ab.data_ptr(), d_hidden.data_ptr(), d_mod.data_ptr(), 3 * D,
+                                   d_w3.data_ptr(), d_b3.data_ptr(), B, L, D, code, st)
+    _cabi.check(s, "dm_spiral_post_mix_bwd")
+    d_lnab = torch.mm(d_hidden, att_w)                                        # (rows, 2D) act dtype
+    d_att_w = torch.mm(d_hidden.t(), lnab).float()                            # (D, 2D)
+    d_att_b = torch.sum(d_hidden, 0, dtype=torch.float32)
+    s = lib.dm_spiral_post_ln_bwd(ab.data_ptr(), _f32c(ln2_weight, "ln2_weight").data_ptr(), d_lnab.data_ptr(),
+                                  d_ab.data_ptr(), d_l2w.data_ptr(), d_l2b.data_ptr(), B, L, D, 1e-5, code, st)
+    _cabi.check(s, "dm_spiral_post_ln_bwd")
+    LAUNCH_COUNTER["kernels"] += 2
+    return d_ab, d_mod, d_l2w, d_l2b, d_att_w, d_att_b, d_w3, d_b3
+
+
+def merge_directions(g_scan: torch.Tensor, plan: ScanPlan, out_dtype) -> Optional[torch.Tensor]:
+    """(G, B, K, L, C) fp32 gradients in scan order -> (G, B, L_src, C) in ``out_dtype``, summed over the K directions
+    (adjoint of the CrossScan gather) in one kernel.  None if some direction is not a full permutation (caller falls
+    back to index_add)."""
+    inv = plan.inverse_table()
+    if inv is None or not g_scan.is_cuda or g_scan.dtype != torch.float32 or g_scan.shape[-1] % 8:
+        return None
+    G, B, K, L, Cc = g_scan.shape
+    idx = getattr(plan, "_flat_inv32", None)
+    if idx is None:
+        dev = g_scan.device
+        cols = [(torch.arange(L, device=dev) if inv[k] is None else inv[k]) + k * L for k in range(K)]
+        idx = torch.stack(cols, 1).reshape(-1).to(torch.int32).contiguous()    # (L_src * K): [l][k]
+        plan._flat_inv32 = idx
+    out = torch.empty((G, B, plan.src_len, Cc), dtype=out_dtype, device=g_scan.device)
+    st = _cabi.lib().dm_merge_directions(g_scan.contiguous().data_ptr(), idx.data_ptr(), out.data_ptr(), G * B, plan.src_len,
+                                         K, K * L, Cc, _dtype_code(out), _stream_handle(g_scan.device))
+    _cabi.check(st, "dm_merge_directions")
+    LAUNCH_COUNTER["kernels"] += 1
+    return out

@@ -217,6 +217,31 @@ int dm_spiral_post_mix_pre(const float* x, const float* skip, const void* ab, co
                            int64_t mod_next_batch_stride, const float* w, void* out2, int32_t batch, int32_t seqlen,
                            int32_t d_model, float eps, int32_t act_dtype, void* stream);
 
+/* Adjoints of the three row kernels above for the training step (autograd of block/mamba_block.py:100-115, reached from
+ * train.py:259).  Per-batch-element and per-parameter gradients are ACCUMULATED (atomics) into buffers the caller zeroed:
+ *   dm_spiral_pre_bwd       d_out2 (2, rows, d) act dtype -> dx (rows, d) fp32 [= d skip]; d_mod[:, 0:d] += d shift,
+ *                           d_mod[:, d:2d] += d scale; d_ln_weight / d_ln_bias (d) += .  w == NULL: mask of ones.
+ *   dm_spiral_post_mix_bwd  d_x_out (rows, d) fp32 [= d x = d skip] -> d_ab (2, rows, d) and d_hidden (rows, d) act dtype
+ *                           (overwritten); d_mod[:, 2d:3d] += d gate; d_w3 (d) +=, d_b3 (1) += .
+ *   dm_spiral_post_ln_bwd   d_out (rows, 2d) act dtype -> d_ab += LayerNorm backward; d_ln_weight / d_ln_bias (2d) += . */
+int dm_spiral_pre_bwd(const float* x, const float* skip, const float* ln_weight, const float* ln_bias, const float* mod,
+                      int64_t mod_batch_stride, const float* w, const void* d_out2, float* dx, float* d_mod,
+                      int64_t d_mod_batch_stride, float* d_ln_weight, float* d_ln_bias, int32_t batch, int32_t seqlen,
+                      int32_t d_model, float eps, int32_t act_dtype, void* stream);
+int dm_spiral_post_mix_bwd(const float* d_x_out, const void* ab, const void* hidden, const float* w3, const float* b3,
+                           const float* mod, int64_t mod_batch_stride, void* d_ab, void* d_hidden, float* d_mod,
+                           int64_t d_mod_batch_stride, float* d_w3, float* d_b3, int32_t batch, int32_t seqlen,
+                           int32_t d_model, int32_t act_dtype, void* stream);
+int dm_spiral_post_ln_bwd(const void* ab, const float* ln_weight, const void* d_out, void* d_ab, float* d_ln_weight,
+                          float* d_ln_bias, int32_t batch, int32_t seqlen, int32_t d_model, float eps, int32_t act_dtype,
+                          void* stream);
+
+/* Adjoint of the CrossScan gather (reference block/mamba.py:48-57): dst[r][l][:] = sum_k src[r][index[l*n_dir + k]][:].
+ * src (n_groups, rows_per_group, channels) fp32 scan-order rows, index (src_len * n_dir) int32 row numbers inside a group,
+ * dst (n_groups, src_len, channels) act dtype.  channels % 8 == 0. */
+int dm_merge_directions(const float* src, const int32_t* index, void* dst, int32_t n_groups, int32_t src_len,
+                        int32_t n_dir, int32_t rows_per_group, int32_t channels, int32_t act_dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * One reverse-diffusion update as one elementwise kernel (reference diffusion/gaussian_diffusion.py p_mean_variance
  * :254-332 with LEARNED_RANGE variance + epsilon prediction, and p_sample :376-417):
@@ -273,8 +298,8 @@ int dm_gemm_bf16_tn_ex(const dm_gemm_args* args, void* stream);
  * buffers may be passed (per gradient bucket, as soon as its all-reduce has landed).
  * ---------------------------------------------------------------------------------------------------- */
 int dm_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, const float* step,
-                      int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float ema_decay,
-                      float grad_scale, void* stream);
+                      int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay, double ema_decay,
+                      double grad_scale, void* stream);   /* hyper-parameters in double: 1 - beta etc. are formed before rounding */
 
 /* ------------------------------------------------------------------------------------------------------ */
 int dm_version(void);                     /* DM_ABI_VERSION of the loaded library                        */

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
 CKPT = os.path.join(REF, "pretrain_ct_vision_embedder", "brain_patch_size_2.pt")
 
-pytestmark = pytest.mark.skipif(not os.path.exists(CKPT), reason="reference checkout with shipped checkpoints not present")
+needs_ref = pytest.mark.skipif(not os.path.exists(CKPT), reason="reference checkout with shipped checkpoints not present")
 
 
 def _load():
@@ -20,6 +20,7 @@ def _load():
     return torch.load(CKPT, map_location="cpu", weights_only=True)
 
 
+@needs_ref
 def test_shipped_ct_embedder_checkpoint_loads_strict_and_matches_reference_forward():
     """The CT soft-mask embedder shipped with the reference ({model, ema, opt, args}; train_embedder.py) loads with
     strict=True into diffma_b200.ct_encoder.CT_Encoder and produces the reference module's outputs."""
@@ -44,6 +45,7 @@ def test_shipped_ct_embedder_checkpoint_loads_strict_and_matches_reference_forwa
     np.testing.assert_allclose(y1.numpy(), y0.numpy(), rtol=1e-4, atol=1e-5)
 
 
+@needs_ref
 def test_reference_model_state_dict_loads_into_mirror():
     """A state dict produced by the reference's own DiffMa (built over the product shims) loads with strict=True into
     diffma_b200.model.DiffMa for both mixer generations (keys AND shapes)."""
@@ -62,3 +64,45 @@ def test_reference_model_state_dict_loads_into_mirror():
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([shims, ROOT, REF]))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]
+
+
+def test_diffma_checkpoint_roundtrip_in_reference_format(tmp_path):
+    """{model, ema, opt, args} as train.py:293-300 writes it: saved from a FlatTrainState, read back the way sample.py's
+    find_model does (--load-ckpt-type ema | model), and the ``opt`` entry loads into a stock torch.optim.AdamW."""
+    from diffma_b200 import checkpoint, model as M
+    from diffma_b200.ddp import FlatTrainState
+    torch.manual_seed(0)
+    net = M.DiffMa_models["DiffMa-S/7"](input_size=28, dt_rank=16, d_state=16, use_mamba2=False)
+    st = FlatTrainState(net.parameters(), 1, ema_decay=0.5)
+    with torch.no_grad():                                   # pretend one optimizer step happened (no GPU here)
+        st.flat_p.add_(0.01)
+        st.ema.mul_(0.5).add_(st.flat_p, alpha=0.5)
+        st.exp_avg.normal_()
+        st.exp_avg_sq.uniform_()
+        st.step_t.fill_(3.0)
+    path = str(tmp_path / "0000003.pt")
+    checkpoint.save_checkpoint(path, net, st, argparse.Namespace(model="DiffMa-S/7", image_size=224))
+    ck = checkpoint.read(path)
+    assert set(ck) == {"model", "ema", "opt", "args"} and ck["args"].model == "DiffMa-S/7"
+    assert sorted(ck["model"]) == sorted(net.state_dict()) == sorted(ck["ema"])
+    k = "blocks.1.mamba1.in_proj.weight"
+    torch.testing.assert_close(ck["ema"][k], ck["model"][k] - 0.005)
+    # sample.py:19-27 find_model + model.load_state_dict
+    fresh = M.DiffMa_models["DiffMa-S/7"](input_size=28, dt_rank=16, d_state=16, use_mamba2=False)
+    checkpoint.load_checkpoint(path, fresh, kind="ema")
+    torch.testing.assert_close(fresh.state_dict()[k], ck["ema"][k])
+    checkpoint.load_checkpoint({("module." + n): v for n, v in ck["model"].items()}, fresh, kind="model")   # bare, DDP-prefixed
+    torch.testing.assert_close(fresh.state_dict()[k], ck["model"][k])
+    # the optimizer entry is a torch.optim.AdamW state dict (train.py:201), and resumes a FlatTrainState
+    opt = torch.optim.AdamW(fresh.parameters(), lr=1e-4, weight_decay=0)
+    opt.load_state_dict(ck["opt"])
+    p0 = next(p for p in fresh.parameters() if p.requires_grad)
+    assert len(opt.state) == sum(p.requires_grad for p in fresh.parameters())      # frozen pos_embed: in the group, no state
+    assert float(opt.state[p0]["step"]) == 3.0
+    st2 = FlatTrainState(fresh.parameters(), 1, ema_decay=0.5)
+    checkpoint.load_adamw_state(fresh, st2, ck["opt"])
+    back = checkpoint.adamw_state_dict(fresh, st2)["state"]            # per-parameter views (the flat buffers also hold padding)
+    for i, e in ck["opt"]["state"].items():
+        torch.testing.assert_close(back[i]["exp_avg"], e["exp_avg"])
+        torch.testing.assert_close(back[i]["exp_avg_sq"], e["exp_avg_sq"])
+    assert float(st2.step_t) == 3.0

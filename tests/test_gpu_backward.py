@@ -207,3 +207,77 @@ def test_mamba2_training_step_bf16_runs(dev):
               "blocks.1.mamba2.conv1d.weight", "blocks.0.mamba1.dt_bias", "blocks.2.mamba1.norm.weight"):
         cos = torch.nn.functional.cosine_similarity(grads["fp32"][n], grads["bf16"][n], dim=0).item()
         assert cos > 0.97, (n, cos)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused training path of the Spiral block (row kernels + hand-written adjoints, csrc/dm_block_bwd.cu) vs torch autograd of
+# the op-by-op module path (reference block/mamba_block.py:100-115 differentiated by autograd)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,side,with_skip,with_w", [(3, 7, True, True), (2, 14, False, True), (5, 4, True, False)])
+def test_fused_train_block_grads_match_module_path_fp32(dev, monkeypatch, B, side, with_skip, with_w):
+    from diffma_b200 import blocks, scan_orders, synth
+    L = side * side
+    ml, inv = scan_orders.spiral(side)
+    torch.manual_seed(0)
+    blk = blocks.Spiral_MambaBlock(D_dim=512, E_dim=1024, dt_rank=16, dim_inner=1024, d_state=16, token_list=ml[2],
+                                   token_list_reversal=ml[3], origina_list=inv[2], origina_list_reversal=inv[3],
+                                   use_mamba2=False)
+    synth.fill_trained_like_(blk, seed=3)
+    blk = blk.to(dev).train()
+    g = torch.Generator().manual_seed(B * 100 + side)
+    x0 = torch.randn(B, L, 512, generator=g).to(dev)
+    s0 = torch.randn(B, L, 512, generator=g).to(dev) * 0.5
+    c0 = torch.randn(B, 1024, generator=g).to(dev)
+    w = torch.sigmoid(torch.randn(B, L, 1, generator=g)).to(dev) if with_w else None
+    gout = torch.randn(B, L, 512, generator=g).to(dev)
+    res = {}
+    for fused in (False, True):
+        monkeypatch.setattr(blocks, "_FUSED_TRAIN", fused)
+        blk.zero_grad(set_to_none=True)
+        with torch.enable_grad():
+            x = x0.clone().requires_grad_(True)
+            sk = s0.clone().requires_grad_(True) if with_skip else None
+            c = c0.clone().requires_grad_(True)
+            out = blk(x, c, w, skip=sk) if with_skip else blk(x, c, w)
+            out.backward(gout)
+        res[fused] = dict(out=out.detach(), dx=x.grad, dc=c.grad, dskip=None if sk is None else sk.grad,
+                          **{n: p.grad.clone() for n, p in blk.named_parameters()})
+    torch.set_grad_enabled(False)
+    for k, ref in res[False].items():
+        if ref is None:
+            continue
+        got = res[True][k]
+        assert got is not None, k
+        assert _relerr(got, ref) < 2e-3, (k, _relerr(got, ref))
+
+
+def test_fused_train_model_step_matches_module_path(dev, monkeypatch):
+    """DiffMa-S/4 training loss + backward: fused training path vs module path, fp32 (tight) and bf16 autocast (the two
+    paths round differently: cosine of the big gradient tensors)."""
+    from diffma_b200 import blocks, create_model_and_diffusion, synth
+    for mode in ("fp32", "bf16"):
+        grads, losses = {}, {}
+        for fused in (False, True):
+            monkeypatch.setattr(blocks, "_FUSED_TRAIN", fused)
+            torch.manual_seed(0)
+            net, diffusion = create_model_and_diffusion("DiffMa-S/4", respacing="")
+            synth.fill_trained_like_(net, seed=11)
+            net = net.to(dev).train()
+            b = synth.synthetic_batch(4, tokens=49, seed=9, device=dev)
+            t = torch.tensor([10, 200, 500, 900], device=dev)
+            noise = torch.randn(4, 4, 28, 28, generator=torch.Generator().manual_seed(1)).to(dev)
+            with torch.enable_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+                loss = diffusion.training_losses(net, b["x"], t, dict(y=b["y"], y2=b["y2"], w=b["w"]), noise=noise)["loss"].mean()
+                loss.backward()
+            losses[fused] = float(loss)
+            grads[fused] = {n: p.grad.detach().float() for n, p in net.named_parameters() if p.grad is not None}
+        torch.set_grad_enabled(False)
+        assert set(grads[True]) == set(grads[False])
+        assert abs(losses[True] - losses[False]) < (1e-4 if mode == "fp32" else 2e-2) * max(1.0, abs(losses[False]))
+        for n, ref in grads[False].items():
+            got = grads[True][n]
+            if mode == "fp32":
+                assert _relerr(got, ref) < 3e-3, (n, _relerr(got, ref))
+            elif ref.numel() >= 4096:
+                cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+                assert cos > 0.97, (n, cos)

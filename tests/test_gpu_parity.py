@@ -283,11 +283,14 @@ def test_gated_scan_equals_scan_with_silu_inside(dev):
                 ops.mamba1_scan([gz.requires_grad_(True)], [w], plan, z_gated=True)
 
 
-def test_tcgen05_gemm_path_in_block(dev, monkeypatch):
-    """The fused block with DIFFMA_GEMM=tcgen05 (projections on dm_gemm_bf16_tn) equals the library-GEMM path."""
+@pytest.mark.parametrize("use_m2", [False, True])
+def test_tcgen05_gemm_path_in_block(dev, monkeypatch, use_m2):
+    """The fused block with DIFFMA_GEMM=tcgen05 (in-projection with the SiLU(z) epilogue + gated scan, out-projection with
+    the summed-A producer / rstd row scale, attention Linear with bias: all on dm_gemm_bf16_tn_ex) equals the
+    library-GEMM path."""
     from diffma_b200 import blocks, model as M, synth
     torch.manual_seed(0)
-    net = M.DiffMa_models["DiffMa-S/2"](input_size=28, dt_rank=16, d_state=16, use_mamba2=False).eval()
+    net = M.DiffMa_models["DiffMa-S/2"](input_size=28, dt_rank=16, d_state=16, use_mamba2=use_m2).eval()
     synth.fill_trained_like_(net, seed=11)
     net = net.to(dev)
     b = synth.synthetic_batch(2, tokens=196, seed=21, device=dev)

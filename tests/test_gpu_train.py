@@ -61,7 +61,8 @@ def test_captured_training_step_runs_and_updates_weights(dev):
     import train_bench
     from diffma_b200 import ops
     e0 = ops.weights_epoch()
-    res = train_bench.run(model="DiffMa-S/4", batch=4, steps=3, warmup=3, world=1, rank=0, device=dev)
+    with torch.enable_grad():                              # other test modules switch grad mode off process-wide
+        res = train_bench.run(model="DiffMa-S/4", batch=4, steps=3, warmup=3, world=1, rank=0, device=dev)
     assert res["cuda_graph"] is True, res["capture_note"]
     assert res["loss"] == res["loss"] and 0 < res["loss"] < 10
     assert res["value"] > 0 and res["n_gpus"] == 1 and res["exposed_allreduce_ms"] is None
@@ -80,13 +81,14 @@ def test_flat_train_state_matches_torch_adamw_and_ema(dev):
     state = FlatTrainState(net.parameters(), 1, lr=1e-3, ema_decay=0.99)
     x = torch.randn(8, 33, device=dev)
     for _ in range(3):
-        state.begin_step()
-        net(x).square().mean().backward()
-        state.finish_backward()
-        state.optimizer_step()
-        opt.zero_grad()
-        ref(x).square().mean().backward()
-        opt.step()
+        with torch.enable_grad():
+            state.begin_step()
+            net(x).square().mean().backward()
+            state.finish_backward()
+            state.optimizer_step()
+            opt.zero_grad()
+            ref(x).square().mean().backward()
+            opt.step()
         with torch.no_grad():
             for pe, pr in zip(ema_ref.parameters(), ref.parameters()):
                 pe.mul_(0.99).add_(pr, alpha=0.01)

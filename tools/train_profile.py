@@ -45,9 +45,15 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step()
     torch.cuda.synchronize()
+# device time by the ATen / autograd op that launched the kernels (which part of the eager glue costs what)
+ops_rows = []
+for e in sorted(prof.key_averages(), key=lambda e: -getattr(e, "self_device_time_total", 0))[:40]:
+    t = getattr(e, "self_device_time_total", 0)
+    if t > 0:
+        ops_rows.append({"op": e.key[:60], "calls": e.count, "self_device_us": round(t, 1)})
 agg = collections.Counter()
 cnt = collections.Counter()
 for e in prof.events():
@@ -59,4 +65,4 @@ for e in prof.events():
 total = sum(agg.values())
 rows = [{"kernel": k[:70], "count": cnt[k], "us": round(v, 1), "share": round(100 * v / total, 1)} for k, v in agg.most_common(22)]
 print(json.dumps({"model": a.model, "batch": a.batch, "mamba2": a.mamba2, "device_time_us": round(total, 1),
-                  "launches": sum(cnt.values()), "top": rows}, indent=1))
+                  "launches": sum(cnt.values()), "top": rows, "by_op": ops_rows}, indent=1))
