@@ -69,8 +69,10 @@ class Spiral_MambaBlock(nn.Module):
                 and x.is_contiguous()):
             return self._forward_fused(x, c, w, skip)
         if (_FUSED_TRAIN and torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 512
-                and x.is_contiguous() and (w is None or not w.requires_grad)):
-            return self._forward_train_fused(x, c, w, skip)
+                and w is not None and not w.requires_grad):
+            # (the patch embedding hands over a transposed view, and elementwise results inherit its strides: one copy
+            # here puts the whole residual stream into the row-major layout the row kernels read)
+            return self._forward_train_fused(x.contiguous(), c, w, skip)
         if skip is not None:
             x = x + skip
         shift, scale, gate = self.adaLN_modulation(c).chunk(3, dim=1)

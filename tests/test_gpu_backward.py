@@ -213,7 +213,7 @@ def test_mamba2_training_step_bf16_runs(dev):
 # fused training path of the Spiral block (row kernels + hand-written adjoints, csrc/dm_block_bwd.cu) vs torch autograd of
 # the op-by-op module path (reference block/mamba_block.py:100-115 differentiated by autograd)
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,side,with_skip,with_w", [(3, 7, True, True), (2, 14, False, True), (5, 4, True, False)])
+@pytest.mark.parametrize("B,side,with_skip,with_w", [(3, 7, True, True), (2, 14, False, True), (5, 4, True, True)])
 def test_fused_train_block_grads_match_module_path_fp32(dev, monkeypatch, B, side, with_skip, with_w):
     from diffma_b200 import blocks, scan_orders, synth
     L = side * side
@@ -266,9 +266,14 @@ def test_fused_train_model_step_matches_module_path(dev, monkeypatch):
             b = synth.synthetic_batch(4, tokens=49, seed=9, device=dev)
             t = torch.tensor([10, 200, 500, 900], device=dev)
             noise = torch.randn(4, 4, 28, 28, generator=torch.Generator().manual_seed(1)).to(dev)
+            from diffma_b200 import ops
+            n0 = ops.LAUNCH_COUNTER["kernels"]
             with torch.enable_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
                 loss = diffusion.training_losses(net, b["x"], t, dict(y=b["y"], y2=b["y2"], w=b["w"]), noise=noise)["loss"].mean()
                 loss.backward()
+            launched = ops.LAUNCH_COUNTER["kernels"] - n0
+            # 4 blocks: scan fwd (2) + bwd (2) + merge (1) always; the fused path adds pre, post_ln, post_mix + 3 adjoints
+            assert launched >= (4 * 11 if fused else 4 * 5), (fused, launched)
             losses[fused] = float(loss)
             grads[fused] = {n: p.grad.detach().float() for n, p in net.named_parameters() if p.grad is not None}
         torch.set_grad_enabled(False)

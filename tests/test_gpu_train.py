@@ -45,7 +45,7 @@ def test_adamw_ema_kernel_matches_oracle(dev, n, wd, ema_on):
                                                              weight_decay=wd, ema_decay=0.999, grad_scale=0.5)
         re_[:n] = ne
         torch.testing.assert_close(P.cpu().double()[:n], rp[:n], rtol=2e-6, atol=2e-6)
-        torch.testing.assert_close(M.cpu().double()[:n], rm[:n], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(M.cpu().double()[:n], rm[:n], rtol=1e-5, atol=2e-6)   # fp32 rounding of O(1..10) terms that nearly cancel
         torch.testing.assert_close(V.cpu().double()[:n], rv[:n], rtol=1e-5, atol=1e-9)
         if ema_on:
             torch.testing.assert_close(E.cpu().double()[:n], re_[:n], rtol=2e-6, atol=2e-6)
