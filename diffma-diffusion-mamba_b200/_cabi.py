@@ -15,7 +15,7 @@ DM_F32, DM_BF16 = 0, 1
 DM_MAX_GROUPS = 4
 DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
-EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba1_bwd_chunk_tokens", "dm_mamba2_ssd_fwd", "dm_spiral_pre", "dm_spiral_post_ln",
+EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba1_bwd_chunk_tokens", "dm_mamba2_ssd_fwd", "dm_mamba2_ssd_bwd", "dm_merge_directions_multi", "dm_spiral_pre", "dm_spiral_post_ln",
            "dm_spiral_post_mix", "dm_spiral_post_mix_pre", "dm_spiral_pre_bwd", "dm_spiral_post_mix_bwd", "dm_spiral_post_ln_bwd",
            "dm_merge_directions", "dm_gemm_bf16_tn", "dm_gemm_bf16_tn_ex", "dm_p_sample_update", "dm_adamw_ema_step", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
@@ -70,6 +70,14 @@ class Mamba2Group(C.Structure):
         ("conv_weight", C.c_void_p), ("conv_bias", C.c_void_p), ("dt_bias", C.c_void_p), ("A", C.c_void_p),
         ("D", C.c_void_p),
     ]
+
+
+class Mamba2BwdGroup(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("u", "x_dbl", "d_x_dbl", "d_bc", "d_conv_weight", "d_conv_bias")]
+
+
+class MergeSegment(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("channels", C.c_int32), ("row_stride", C.c_int32)]
 
 
 class Mamba2Args(C.Structure):
@@ -134,6 +142,10 @@ def lib() -> C.CDLL:
     L.dm_spiral_post_ln_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]
     L.dm_merge_directions.restype = C.c_int
     L.dm_merge_directions.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.dm_merge_directions_multi.restype = C.c_int
+    L.dm_merge_directions_multi.argtypes = [C.POINTER(MergeSegment), i32, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.dm_mamba2_ssd_bwd.restype = C.c_int
+    L.dm_mamba2_ssd_bwd.argtypes = [C.POINTER(Mamba2Args), C.POINTER(Mamba2BwdGroup), C.c_int, vp]
     L.dm_gemm_bf16_tn.restype = C.c_int
     L.dm_gemm_bf16_tn.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i32, vp]
     L.dm_gemm_bf16_tn_ex.restype = C.c_int

@@ -18,6 +18,12 @@ import torch
 
 from . import _cabi, ops
 
+import os
+
+# DIFFMA_M2_BWD=torch: differentiate the Mamba-2 conv / gathers with torch ops around the reverse-scan kernel (round-1
+# path, kept for A/B runs and as the checker of the CUDA orchestration)
+_M2_BWD_CUDA = os.environ.get("DIFFMA_M2_BWD", "cuda") != "torch"
+
 _W1 = ("conv_weight", "conv_bias", "x_proj_weight", "dt_proj_weight", "dt_bias", "A", "D")
 _W2 = ("conv_weight", "conv_bias", "dt_bias", "A", "D")
 
@@ -304,6 +310,144 @@ def mamba2_backward(zx, weights, plan, d_inner, d_state, nheads, v, gv, gss, s6_
     return dzx, grads
 
 
+def mamba2_backward_cuda(zx, weights, plan, d_inner, d_state, nheads, v, gv, gss):
+    """``mamba2_backward`` on the C-ABI only (no torch conv / gather / cat): ``dm_mamba2_ssd_bwd`` phase 0 (operand
+    preparation) -> ``dm_mamba1_scan_bwd`` phases 1 + 2 on the SSD operands (reverse scan, conv backward of x) ->
+    ``dm_mamba2_ssd_bwd`` phase 2 (conv backward of B | C) -> per-head reductions -> ``dm_merge_directions_multi``
+    ([dz | dx | dB dC | d dt] un-permuted and summed over the directions).  Same return value as ``mamba2_backward``.
+    Returns None when the plan is not a set of full permutations (caller falls back to the torch glue)."""
+    inv = plan.inverse_table()
+    G = len(zx)
+    D, N, H = d_inner, d_state, nheads
+    if inv is None or H > 32 or N != 16 or D % 128 or plan.layout not in ("concat", "stacked"):
+        return None
+    P = D // H
+    R, E = 32, 64
+    Cc = D + 2 * N
+    x0 = zx[0]
+    dev, act = x0.device, x0.dtype
+    B, Lsrc, Cin = x0.shape
+    K, L = plan.n_dir, plan.seqlen
+    f32 = dict(dtype=torch.float32, device=dev)
+    es = x0.element_size()
+    # total gradient of v: direct + through sumsq = sum_c v^2 (the RMSNorm statistic the forward hands out)
+    dv = gv
+    if gss is not None:
+        g2s = gss.float()
+        g2s = g2s.transpose(2, 3).unsqueeze(-1) if plan.layout == "concat" else g2s.unsqueeze(-1)   # -> v's row layout
+        dv = torch.addcmul(gv.float(), v.float(), g2s, value=2.0)
+    dv = dv.to(act).contiguous()                                              # plan.out_shape: (G,B,L_src,K,D) | (G,B,K,L,D)
+    lib, st = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    # ---- phase 0: u, x_dbl ------------------------------------------------------------------------------------
+    u = torch.empty((G, B, K, L, D), dtype=act, device=dev)
+    x_dbl = torch.empty((G, B, K, L, E), **f32)
+    a2 = _cabi.Mamba2Args()
+    a2.batch, a2.n_dir, a2.seqlen = B, K, L
+    a2.d_inner, a2.d_state, a2.nheads, a2.d_conv = D, N, H, weights[0].conv_weight.shape[1]
+    a2.act_dtype, a2.out_order, a2.n_groups, a2.gate = ops._dtype_code(x0), plan.out_order, G, 1
+    a2.order = ops._ptr(plan.table)
+    ct = int(lib.dm_mamba1_bwd_chunk_tokens())
+    nch = (L + ct - 1) // ct
+    d_xz_scan = torch.empty((G, B, K, L, 2 * D), **f32)
+    du = torch.empty((G, B, K, L, D), **f32)
+    ddelta = torch.empty((G, B, K, L, D), **f32)
+    ws = torch.empty((G, B, K, nch, D, N), **f32)
+    d_bc = torch.empty((G, B, K, L, 2 * N), **f32)
+    sizes = [G * B * K * L * E, G * D * N, G * D, G * D, G * Cc * 4, G * Cc]
+    acc = torch.zeros(sum(sizes), **f32)                                      # every accumulated buffer: one memset
+    d_x_dbl, dA, dD, ddtb, dcw, dcb = (t.view(shape) for t, shape in zip(
+        acc.split(sizes), [(G, B, K, L, E), (G, D, N), (G, D), (G, D), (G, Cc, 4), (G, Cc)]))
+    g2 = (_cabi.Mamba2BwdGroup * G)()
+    bs, ts = ops._strides(x0)
+    for g in range(G):
+        x, w = zx[g], weights[g]
+        if x.shape != x0.shape or x.dtype != act or x.stride(2) != 1 or ops._strides(x) != (bs, ts):
+            return None
+        gs = a2.group[g]
+        gs.zxbcdt, gs.in_batch_stride, gs.in_token_stride = x.data_ptr(), bs, ts
+        gs.conv_weight = w.conv_weight.data_ptr()
+        gs.conv_bias = ops._ptr(w.conv_bias)
+        g2[g].u, g2[g].x_dbl = u[g].data_ptr(), x_dbl[g].data_ptr()
+        g2[g].d_x_dbl, g2[g].d_bc = d_x_dbl[g].data_ptr(), d_bc[g].data_ptr()
+        g2[g].d_conv_weight = dcw[g].data_ptr()
+        g2[g].d_conv_bias = dcb[g].data_ptr() if w.conv_bias is not None else None
+    _cabi.check(lib.dm_mamba2_ssd_bwd(C.byref(a2), g2, 0, st), "dm_mamba2_ssd_bwd(phase 0)")
+    # ---- the S6 view of the SSD operands: one-hot dt_proj, per-channel A / D / dt_bias (tiny, built on the device) ----
+    head = torch.arange(D, device=dev) // P
+    onehot = (torch.arange(R, device=dev)[None, :] == head[:, None]).to(act).contiguous()       # (D, 32)
+    a1 = _cabi.Mamba1Args()
+    a1.batch, a1.n_dir, a1.seqlen = B, K, L
+    a1.d_inner, a1.d_state, a1.dt_rank, a1.d_conv = D, N, R, 4
+    a1.act_dtype, a1.out_order, a1.n_groups = ops._dtype_code(x0), plan.out_order, G
+    a1.order = ops._ptr(plan.table)
+    obs, ods, ots = plan.out_strides(D)
+    gr = (_cabi.Mamba1BwdGroup * G)()
+    keep = []
+    for g in range(G):
+        w = weights[g]
+        A_c = w.A.float()[head].unsqueeze(1).expand(D, N).contiguous()
+        D_c = None if w.D is None else w.D.float()[head].contiguous()
+        b_c = None if w.dt_bias is None else w.dt_bias.float()[head].contiguous()
+        keep += [A_c, D_c, b_c]
+        gs = a1.group[g]
+        gs.xz = zx[g].data_ptr() - D * es                 # z of [z | x | ...] lands at the S6 layout's offset d_inner
+        gs.xz_batch_stride, gs.xz_token_stride = bs, ts
+        gs.out, gs.out_batch_stride, gs.out_dir_stride, gs.out_token_stride = dv[g].data_ptr(), obs, ods, ots
+        gs.u, gs.x_dbl = u[g].data_ptr(), x_dbl[g].data_ptr()
+        gs.conv_weight, gs.conv_bias = w.conv_weight.data_ptr(), ops._ptr(w.conv_bias)
+        gs.x_proj_weight = onehot.data_ptr()              # unused by the backward kernels (validated non-null only)
+        gs.dt_proj_weight = onehot.data_ptr()
+        gs.dt_bias, gs.A, gs.D = ops._ptr(b_c), A_c.data_ptr(), ops._ptr(D_c)
+        r = gr[g]
+        r.dout = dv[g].data_ptr()
+        r.d_xz_scan, r.du, r.ddelta = d_xz_scan[g].data_ptr(), du[g].data_ptr(), ddelta[g].data_ptr()
+        r.d_x_dbl, r.dA = d_x_dbl[g].data_ptr(), dA[g].data_ptr()
+        r.dD = dD[g].data_ptr() if w.D is not None else None
+        r.d_dt_bias = ddtb[g].data_ptr() if w.dt_bias is not None else None
+        r.state_workspace, r.states_valid = ws[g].data_ptr(), 0
+        r.d_conv_weight = dcw[g].data_ptr()               # rows [0, D) of the (Cc, 4) buffer
+        r.d_conv_bias = dcb[g].data_ptr() if w.conv_bias is not None else None
+    _cabi.check(lib.dm_mamba1_scan_bwd(C.byref(a1), gr, 1, st), "dm_mamba1_scan_bwd(phase 1, SSD operands)")
+    for g in range(G):
+        a1.group[g].xz = zx[g].data_ptr() + D * es        # x of [z | x | ...] at offset 0 for the conv backward
+    _cabi.check(lib.dm_mamba1_scan_bwd(C.byref(a1), gr, 2, st), "dm_mamba1_scan_bwd(phase 2, SSD operands)")
+    _cabi.check(lib.dm_mamba2_ssd_bwd(C.byref(a2), g2, 2, st), "dm_mamba2_ssd_bwd(phase 2)")
+    ops.LAUNCH_COUNTER["kernels"] += 4
+    # ---- per-head reductions, merge of the directions ---------------------------------------------------------
+    ddt = ddelta.view(G, B, K, L, H, P).sum(-1)                                # (G, B, K, L, H) d (raw dt)
+    Hp = (H + 7) // 8 * 8
+    if Hp != H:
+        ddt = torch.nn.functional.pad(ddt, (0, Hp - H))
+    ddt = ddt.contiguous()
+    idx = getattr(plan, "_flat_inv32", None)
+    if idx is None:
+        cols = [(torch.arange(L, device=dev) if inv[k] is None else inv[k]) + k * L for k in range(K)]
+        idx = torch.stack(cols, 1).reshape(-1).to(torch.int32).contiguous()
+        plan._flat_inv32 = idx
+    total = 2 * D + 2 * N + Hp
+    out = torch.empty((G, B, Lsrc, total), dtype=act, device=dev)
+    segs = (_cabi.MergeSegment * 4)()
+    base = d_xz_scan.data_ptr()
+    for i, (ptr, ch, rs) in enumerate(((base + D * 4, D, 2 * D), (base, D, 2 * D), (d_bc.data_ptr(), 2 * N, 2 * N),
+                                       (ddt.data_ptr(), Hp, Hp))):
+        segs[i].src, segs[i].channels, segs[i].row_stride = ptr, ch, rs
+    _cabi.check(lib.dm_merge_directions_multi(segs, 4, idx.data_ptr(), out.data_ptr(), G * B, Lsrc, K, K * L,
+                                              ops._dtype_code(out), st), "dm_merge_directions_multi")
+    ops.LAUNCH_COUNTER["kernels"] += 1
+    dzx = [out[g][..., :Cin] if total != Cin else out[g] for g in range(G)]
+    grads = []
+    for g in range(G):
+        w = weights[g]
+        if w.dt_bias is None:
+            db_h = None
+        else:
+            db_h = ddtb[g].view(H, P).sum(-1)
+        per = {"conv_weight": dcw[g], "conv_bias": dcb[g] if w.conv_bias is not None else None, "dt_bias": db_h,
+               "A": dA[g].view(H, P * N).sum(-1), "D": None if w.D is None else dD[g].view(H, P).sum(-1)}
+        grads += [per[f] for f in _W2]
+    return dzx, grads
+
+
 class Mamba2SsdFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, G, d_inner, d_state, nheads, gate, want_sumsq, *tensors):
@@ -334,8 +478,12 @@ class Mamba2SsdFn(torch.autograd.Function):
         n = len(_W2)
         weights = [ops.Mamba2Weights(*flat[g * n:(g + 1) * n]) for g in range(G)]
         d_inner, d_state, nheads = ctx.dims
-        dzx, grads = mamba2_backward(zx, weights, plan, d_inner, d_state, nheads, v, gv,
-                                     gss if ctx.want_sumsq else None)
+        res = None
+        if zx[0].is_cuda and _M2_BWD_CUDA:
+            res = mamba2_backward_cuda(zx, weights, plan, d_inner, d_state, nheads, v, gv, gss if ctx.want_sumsq else None)
+        if res is None:         # partial-cover plans (EfficientVMamba) and the CPU glue tests: torch ops around the scan kernel
+            res = mamba2_backward(zx, weights, plan, d_inner, d_state, nheads, v, gv, gss if ctx.want_sumsq else None)
+        dzx, grads = res
         return (None, None, None, None, None, None, None, *dzx, *grads)
 
 

@@ -539,3 +539,62 @@ extern "C" int dm_merge_directions(const float* src, const int32_t* index, void*
     DM_CUDA_TRY(cudaGetLastError());
     return DM_OK;
 }
+
+namespace dm {
+namespace {
+struct MergeSegs { const float* src[4]; int channels[4]; int row_stride[4]; int n; int total; };
+template <typename T>
+__global__ void __launch_bounds__(256)
+merge_directions_multi_kernel(const MergeSegs sg, const int32_t* __restrict__ idx, T* __restrict__ dst, int Lsrc, int K,
+                              int rows_per_group) {
+    const int l = blockIdx.x, r = blockIdx.y;
+    T* out = dst + (static_cast<int64_t>(r) * Lsrc + l) * sg.total;
+    int col0 = 0;
+    for (int s = 0; s < sg.n; ++s) {
+        const float* base = sg.src[s] + static_cast<int64_t>(r) * rows_per_group * sg.row_stride[s];
+        for (int c = threadIdx.x * 8; c < sg.channels[s]; c += blockDim.x * 8) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < K; ++k) {
+                const int j = __ldg(idx + l * K + k);
+                float v[8];
+                V8b<float>::load(base + static_cast<int64_t>(j) * sg.row_stride[s] + c, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += v[e];
+            }
+            V8b<T>::store(out + col0 + c, acc);
+        }
+        col0 += sg.channels[s];
+    }
+}
+}  // namespace
+}  // namespace dm
+
+extern "C" int dm_merge_directions_multi(const dm_merge_segment* segments, int32_t n_segments, const int32_t* index, void* dst,
+                                         int32_t n_groups, int32_t src_len, int32_t n_dir, int32_t rows_per_group,
+                                         int32_t act_dtype, void* stream) {
+    if (!segments || n_segments <= 0 || n_segments > 4 || !index || !dst || n_groups <= 0 || src_len <= 0 || n_dir <= 0 ||
+        rows_per_group <= 0)
+        return DM_ERR_INVALID_ARG;
+    if (n_groups > 65535) return DM_ERR_UNSUPPORTED;
+    MergeSegs sg{};
+    sg.n = n_segments;
+    for (int s = 0; s < n_segments; ++s) {
+        const dm_merge_segment& m = segments[s];
+        if (!m.src || m.channels <= 0 || m.channels % 8 || m.row_stride % 4 || !aligned16(m.src)) return DM_ERR_INVALID_ARG;
+        sg.src[s] = m.src; sg.channels[s] = m.channels; sg.row_stride[s] = m.row_stride;
+        sg.total += m.channels;
+    }
+    if (!aligned16(dst)) return DM_ERR_INVALID_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 grid(static_cast<unsigned>(src_len), static_cast<unsigned>(n_groups), 1);
+    if (act_dtype == DM_BF16)
+        merge_directions_multi_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(sg, index, static_cast<__nv_bfloat16*>(dst), src_len,
+                                                                           n_dir, rows_per_group);
+    else if (act_dtype == DM_F32)
+        merge_directions_multi_kernel<float><<<grid, 256, 0, st>>>(sg, index, static_cast<float*>(dst), src_len, n_dir,
+                                                                   rows_per_group);
+    else
+        return DM_ERR_UNSUPPORTED;
+    DM_CUDA_TRY(cudaGetLastError());
+    return DM_OK;
+}

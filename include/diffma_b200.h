@@ -190,6 +190,29 @@ typedef struct {
 int dm_mamba2_ssd_fwd(const dm_mamba2_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Mamba-2 backward of dm_mamba2_ssd_fwd (upstream MambaSplitConv1dScanCombinedFn.backward minus the RMSNorm scale and the
+ * out-projection; reference block/mamba2.py:392 differentiated from train.py:258-259 with --use-mamba2).  The SSD
+ * recurrence is the S6 recurrence with A[d, n] = A_head(d), delta[d] = dt_head(d): the reverse scan and the conv backward
+ * of the x channels are dm_mamba1_scan_bwd on SSD operands; this entry point prepares those operands and finishes the
+ * B / C channels.  `args` is the forward's struct; all buffers contiguous, scan order.
+ *   phase 0  conv1d + SiLU of x | B | C in scan order -> u, and x_dbl rows in dm_mamba1's format [dt hi | dt lo | B | C]
+ *            (raw dt of head h in dt_low slot h; the S6 view's dt_proj is the one-hot head map (d_inner, 32));
+ *   then     dm_mamba1_scan_bwd phase 1 with xz = zxbcdt - d_inner (z at offset d_inner), per-channel A / D / dt_bias,
+ *            and phase 2 with xz = zxbcdt + d_inner (x at offset 0), conv_weight = rows [0, d_inner) of the Mamba-2 conv;
+ *   phase 2  conv backward of B | C from d_x_dbl[..., 32:64] -> d_bc, accumulates d_conv_weight / bias rows >= d_inner.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    void* u;                   /* (B, n_dir, seqlen, d_inner) act dtype                      [phase 0 writes]          */
+    float* x_dbl;              /* (B, n_dir, seqlen, 64) fp32                                [phase 0 writes]          */
+    const float* d_x_dbl;      /* (B, n_dir, seqlen, 64) fp32 from the reverse scan          [phase 2 reads]           */
+    float* d_bc;               /* (B, n_dir, seqlen, 2*d_state) fp32: gradient of raw B | C  [phase 2 writes]          */
+    float* d_conv_weight;      /* (d_inner + 2*d_state, d_conv) fp32, accumulated            [phase 2: rows >= d_inner] */
+    float* d_conv_bias;        /* (d_inner + 2*d_state) fp32, accumulated, or NULL                                      */
+} dm_mamba2_bwd_group;
+int dm_mamba2_ssd_bwd(const dm_mamba2_args* args, const dm_mamba2_bwd_group* grads /* [n_groups] */, int phase,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Row-wise glue of Spiral_MambaBlock.forward (reference block/mamba_block.py:100-115), one warp per token row.
  * x / skip / out are the fp32 residual stream (rows = batch*seqlen, d_model = 512 in this build);
  * `mod` is the adaLN output (batch, 3*d_model) = [shift | scale | gate] with row stride mod_batch_stride.
@@ -241,6 +264,13 @@ int dm_spiral_post_ln_bwd(const void* ab, const float* ln_weight, const void* d_
  * dst (n_groups, src_len, channels) act dtype.  channels % 8 == 0. */
 int dm_merge_directions(const float* src, const int32_t* index, void* dst, int32_t n_groups, int32_t src_len,
                         int32_t n_dir, int32_t rows_per_group, int32_t channels, int32_t act_dtype, void* stream);
+/* The same with the output row assembled from up to 4 column segments living in different fp32 tensors (segment s: base
+ * pointer, columns (multiple of 8), source row stride in elements): [dz | dx | dB dC | d dt] of the Mamba-2 backward
+ * without a concatenated (B, n_dir, seqlen, 2096) intermediate. */
+typedef struct { const float* src; int32_t channels; int32_t row_stride; } dm_merge_segment;
+int dm_merge_directions_multi(const dm_merge_segment* segments, int32_t n_segments, const int32_t* index, void* dst,
+                              int32_t n_groups, int32_t src_len, int32_t n_dir, int32_t rows_per_group, int32_t act_dtype,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * One reverse-diffusion update as one elementwise kernel (reference diffusion/gaussian_diffusion.py p_mean_variance

@@ -286,3 +286,33 @@ def test_fused_train_model_step_matches_module_path(dev, monkeypatch):
             elif ref.numel() >= 4096:
                 cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
                 assert cos > 0.97, (n, cos)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_mamba2_backward_cuda_orchestration_equals_torch_glue(dev, monkeypatch, dtype):
+    """dm_mamba2_ssd_bwd (operand preparation + B/C conv backward kernels, dm_merge_directions_multi) around the reverse-scan
+    kernel == the round-1 route (torch conv / gather / cat glue around the same kernel) on a spiral Mamba-2 mixer: every
+    gradient, fp32 tight and bf16 within the rounding of the bf16 outputs."""
+    from diffma_b200 import autograd_ops, mixer, scan_orders, synth
+    ml, inv = scan_orders.spiral(7)
+    kw = dict(token_list=ml[4], token_list_reversal=ml[5], origina_list=inv[4], origina_list_reversal=inv[5])
+    torch.manual_seed(0)
+    m = mixer.Mamba2(d_model=512, d_state=16, d_conv=4, expand=2, **kw)
+    synth.fill_trained_like_(m, seed=5)
+    m = m.to(dev)
+    g = torch.Generator().manual_seed(3)
+    h0 = torch.randn(3, 49, 512, generator=g).to(dev)
+    gout = torch.randn(3, 49, 512, generator=g).to(dev)
+    res = {}
+    for cuda_route in (False, True):
+        monkeypatch.setattr(autograd_ops, "_M2_BWD_CUDA", cuda_route)
+        m.zero_grad(set_to_none=True)
+        with torch.enable_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+            h = h0.clone().requires_grad_(True)
+            out = m(h, "spiral")
+            out.backward(gout.to(out.dtype))
+        res[cuda_route] = dict(h=h.grad.float(), **{n: p.grad.float().clone() for n, p in m.named_parameters()})
+    torch.set_grad_enabled(False)
+    tol = 2e-3 if dtype == torch.float32 else 3e-2
+    for k, ref in res[False].items():
+        assert _relerr(res[True][k], ref) < tol, (k, _relerr(res[True][k], ref))
