@@ -8,7 +8,12 @@ A "step" is one denoising step (``p_sample``: the whole DiffMa forward + posteri
 synthetic latents, bf16 autocast, captured as a CUDA graph.  N>1 (torchrun): every rank runs the same per-GPU
 batch on its own latents (weak scaling, no data-path collective -- sampling shards by batch).
 
-``value``       device-resident images/s over all ranks (CUDA events, barrier + synchronize both sides, max over ranks)
+``value``       device-resident images/s over all ranks (CUDA events, barrier + synchronize both sides, max over ranks);
+                exactly ``--steps`` steps per timed repetition, repeated until >= 0.5 s are timed, median reported
+``configs``     (default run only) the other BASELINE.json configs from the same process: C2 at L=784, C3 (DiffMa-L/2
+                --use-mamba2, batch 32), north_star's scan shape (DiffMa-L/2, batch 32, L=784: kernel time, HBM and MUFU
+                fractions, upstream CUDA kernel), C5's per-GPU step (DiffMa-XXL/2, batch 8) and a short C4 training leg
+                (DiffMa-XL/4, batch 32 per GPU, fwd + bwd + overlapped NCCL all-reduce + AdamW + EMA in one CUDA graph)
 ``e2e``         same step through the public API with HOST (pinned) inputs: H2D of x/t/y/y2/w, step, D2H of the sample;
                 inputs and results double buffered, the host consumes every sample one step behind the device
 ``roofline``    the dominant kernel (m1_scan_kernel / m2_ssd_kernel) timed alone at the workload's shape with L2 flushes
@@ -512,6 +517,11 @@ def main():
         try:
             cfgs["C2_L784"] = side_config(args, device, world, "DiffMa-B/2", 16, 56, False)
             cfgs["C3_mamba2_L2_b32"] = side_config(args, device, world, "DiffMa-L/2", 32, 28, True)
+            c5 = side_config(args, device, world, "DiffMa-XXL/2", 8, 28, False)
+            # BASELINE configs[4]: 250 respaced steps, batch 64 over 8 GPUs = 8 per GPU; the loop is 250 replays of this step
+            c5["p_sample_loop_250_steps_s"] = round(c5["ms_per_step"] * 250 / 1e3, 3)
+            c5["loop_images_per_s"] = round(world * 8 / (c5["ms_per_step"] * 250 / 1e3), 3)
+            cfgs["C5_sampling_XXL2_b8_per_gpu"] = c5
             if rank == 0:
                 # north_star's target: the fused selective scan at DiffMa-L/2, batch 32, L = 784, bf16
                 a2 = argparse.Namespace(**vars(args))

@@ -263,6 +263,16 @@ def mix_groups(mixers: Sequence[nn.Module], inputs: Sequence[torch.Tensor], scan
         for g, m in enumerate(mixers):
             # gated RMSNorm (block/mamba2.py:347-350,402): rstd per (token, direction) row, weight per channel
             rstd = torch.rsqrt(ss[g] / m.d_inner + m.norm.eps)                    # (B, K, rows)
+            if plan.layout == "concat" and m.out_proj.bias is None:
+                # rstd is a per-(token, direction) scalar and the norm weight a per-channel one, so
+                #   sum_k rstd_k (v_k * w_norm) W^T = sum_k rstd_k * (v_k (W * w_norm)^T):
+                # the GEMM consumes v as the kernel wrote it, the norm weight is folded into the (512 x 1024) projection
+                # weight and rstd scales the 512-wide product -- 4x less elementwise traffic than normalising the
+                # (B, L, K, 1024) tensor in fp32, forward and backward (profiles/r02_notes.md).
+                Wn = (m.out_proj.weight.float() * m.norm.weight.float()[None, :]).to(act)
+                o = F.linear(v[g], Wn)                                            # (B, L, K, d_model)
+                outs.append((o * rstd.transpose(1, 2).unsqueeze(-1)).sum(2).to(act))
+                continue
             if plan.layout == "concat":
                 scale = rstd.transpose(1, 2).unsqueeze(-1)                        # (B, L, K, 1)
             elif plan.layout == "disjoint":
