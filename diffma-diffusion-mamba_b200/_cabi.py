@@ -29,7 +29,7 @@ class Mamba1Group(C.Structure):
         ("u", C.c_void_p), ("x_dbl", C.c_void_p),
         ("conv_weight", C.c_void_p), ("conv_bias", C.c_void_p), ("x_proj_weight", C.c_void_p),
         ("dt_proj_weight", C.c_void_p), ("dt_bias", C.c_void_p), ("A", C.c_void_p), ("D", C.c_void_p),
-        ("chunk_states", C.c_void_p),
+        ("chunk_states", C.c_void_p), ("delta", C.c_void_p),
     ]
 
 

@@ -51,6 +51,7 @@ struct M1G {
     const float* A;
     const float* D;
     float* chunk_states;
+    __half* delta;             // optional (seq, L, D) fp16, scan order: softplus(dt_proj(dt_low) + bias), written by kernel P
 };
 
 struct M1P {
@@ -509,7 +510,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
 #define DM_CPL1_MINB 20
 #endif
 // CPL = channels per lane (2 for the big shapes, 1 when there are too few warp-units to fill the SMs otherwise)
-template <typename T, int CPL> struct ScanSmem {
+template <typename T, int CPL, bool kDelta = false> struct ScanSmem {
     static constexpr int kSC = 32 * CPL;     // channels per scan warp
     float xd[2][kCH][kE];                    // x_dbl chunk, rows as above
     T us[2][kCH][kSC];
@@ -517,6 +518,15 @@ template <typename T, int CPL> struct ScanSmem {
     float ds[kCH][kSC + 4];                  // delta_raw tile (token, channel-in-warp)
     int rows[2][kCH];                        // byte offset of each scanned token's output row
     __nv_bfloat16 wdt[sizeof(T) == 4 ? 2 : 1][kSC][kR + 8];   // W_dt slice (hi [, lo]); 80-byte rows: ldmatrix conflict-free
+};
+// delta handed over by kernel P (fp16, softplus already applied): no dt_proj MMA, no W_dt slice, no softplus here
+template <typename T, int CPL> struct ScanSmem<T, CPL, true> {
+    static constexpr int kSC = 32 * CPL;
+    float xd[2][kCH][kE];
+    T us[2][kCH][kSC];
+    T zs[2][kCH][kSC];
+    __half dts[2][kCH][kSC];
+    int rows[2][kCH];
 };
 
 // packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2): halves the issue slots of the recurrence
@@ -631,7 +641,7 @@ __device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
 }
 
 // kGated: z already holds silu(z) (dm_mamba1_args.z_is_gated) -- 18 instead of 19 MUFU per (token, channel)
-template <typename T, int CPL, bool kDyn, bool kSave, bool kGated = false>
+template <typename T, int CPL, bool kDyn, bool kSave, bool kGated = false, bool kDelta = false>
 __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kernel(const __grid_constant__ M1P p, int n_units) {
 #ifdef DM_SCAN_TRACE
     unsigned trace_sm, trace_warp;
@@ -644,7 +654,7 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
     constexpr int kSC = 32 * CPL;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x;
-    ScanSmem<T, CPL>& S = *reinterpret_cast<ScanSmem<T, CPL>*>(smem_raw);
+    ScanSmem<T, CPL, kDelta>& S = *reinterpret_cast<ScanSmem<T, CPL, kDelta>*>(smem_raw);
     const int D = p.D, L = p.L;
     const int slices = D / kSC;
     const int n_chunks = (L + kCH - 1) / kCH;
@@ -685,12 +695,15 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
     const T* u_seq = static_cast<const T*>(G.u) + seq_in_group * L * D + c0;
     const T* z_base = static_cast<const T*>(G.xz) + static_cast<int64_t>(b) * G.xz_bs + D + c0;
     const float* xd_seq = G.x_dbl + seq_in_group * L * kE;
+    const __half* dt_seq = kDelta ? G.delta + seq_in_group * L * D + c0 : nullptr;
     char* out_lane = reinterpret_cast<char*>(static_cast<T*>(G.out) + static_cast<int64_t>(b) * G.out_bs +
                                              static_cast<int64_t>(k) * G.out_ds + c0 + lane);
     const int out_ts32 = static_cast<int>(G.out_ts * sizeof(T));
 
     // ---- W_dt slice -> shared (bf16 hi [, lo]) ----
-    if constexpr (!kSplit) {
+    if constexpr (kDelta) {
+        // nothing to stage: delta arrives per chunk with u and z
+    } else if constexpr (!kSplit) {
         // 16-byte cp.async segments (all in flight at once; completion rides on the first chunk's commit group)
         const char* Wdt = reinterpret_cast<const char*>(static_cast<const T*>(G.wdt) + static_cast<int64_t>(c0) * kR);
 #pragma unroll
@@ -754,6 +767,17 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
             if (part == 0) S.rows[buf][r] = (token_order ? src : j) * out_ts32;
             cp_async16(udst + s * 16, reinterpret_cast<const char*>(u_seq + static_cast<int64_t>(j) * D) + part * 16);
             cp_async16(zdst + s * 16, reinterpret_cast<const char*>(z_base + static_cast<int64_t>(src) * G.xz_ts) + part * 16);
+        }
+        if constexpr (kDelta) {
+            constexpr int kSegD = kSC * 2 / 16;             // 16-byte segments per (token, channels-of-the-warp) fp16 row
+            const uint32_t ddst = smem_u32(&S.dts[buf][0][0]);
+#pragma unroll
+            for (int i = 0; i < kSegD * kCH / 32; ++i) {
+                const int s = lane + 32 * i;
+                const int r = s / kSegD, part = s % kSegD;
+                const int j = min(j0 + r, L - 1);
+                cp_async16(ddst + s * 16, reinterpret_cast<const char*>(dt_seq + static_cast<int64_t>(j) * D) + part * 16);
+            }
         }
         cp_async_commit();
     };
@@ -887,7 +911,7 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
         // ---- delta_raw tile (64 channels x 8 tokens) = W_dt slice (64 x 32) . dt_low^T (32 x 8) on mma.sync m16n8k16:
         //      A = 16 channels x 16 k from shared (ldmatrix), B = the chunk's dt_low rows straight from the staged
         //      x_dbl (token = lane / 4, k pair = lane % 4: exactly the B fragment), hi + lo halves of dt_low ----
-        {
+        if constexpr (!kDelta) {
             const int r = lane >> 2, q = lane & 3;
             const uint32_t* row = reinterpret_cast<const uint32_t*>(&S.xd[buf][r][0]);   // 16 hi words, 16 lo words
             uint32_t b_hi[2][2], b_lo[2][2];
@@ -939,7 +963,10 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
 #pragma unroll
             for (int jj = 0; jj < kCH; ++jj)
 #pragma unroll
-                for (int ch = 0; ch < CPL; ++ch) dtv[jj][ch] = softplus_scaled(fmaf(S.ds[jj][ch * 32 + lane], kLog2e, dtb[ch]));
+                for (int ch = 0; ch < CPL; ++ch) {
+                    if constexpr (kDelta) dtv[jj][ch] = __half2float(S.dts[buf][jj][ch * 32 + lane]);
+                    else dtv[jj][ch] = softplus_scaled(fmaf(S.ds[jj][ch * 32 + lane], kLog2e, dtb[ch]));
+                }
 #pragma unroll
             for (int jj = 0; jj < kCH; ++jj) {
                 if constexpr (kSave) {
@@ -953,7 +980,10 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
             for (int jj = 0; jj < nrows; ++jj) {
                 float dtv[CPL];
 #pragma unroll
-                for (int ch = 0; ch < CPL; ++ch) dtv[ch] = softplus_scaled(fmaf(S.ds[jj][ch * 32 + lane], kLog2e, dtb[ch]));
+                for (int ch = 0; ch < CPL; ++ch) {
+                    if constexpr (kDelta) dtv[ch] = __half2float(S.dts[buf][jj][ch * 32 + lane]);
+                    else dtv[ch] = softplus_scaled(fmaf(S.ds[jj][ch * 32 + lane], kLog2e, dtb[ch]));
+                }
                 if constexpr (kSave) {
                     if (((j0 + jj) % p.save_every) == 0) save_state(j0 + jj);
                 }
@@ -1073,6 +1103,28 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
         static const int force_seg = env_int("DM_SCAN_SEG", 0);   // chunks (of 8 tokens) per work item of the dynamic schedule
         const bool save = p.save_every > 0;       // training forward: checkpoints for the backward, static schedule
         const bool gated = p.z_gated != 0;
+        bool delta_in = !split;                   // delta handed over by kernel P (all groups or none; bf16 only)
+        for (int g = 0; g < p.n_groups; ++g) delta_in = delta_in && p.g[g].delta != nullptr;
+        if (delta_in && !save && !gated) {
+            if constexpr (sizeof(T) == 2) {
+                static PerDeviceOnce dcfg;
+                if (!dcfg.done(dev)) {
+                    DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                    DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                    dcfg.set(dev);
+                }
+                const int units2d = n_seq * (p.D / 64);
+                static const int force_cpl_d = env_int("DM_SCAN_CPL", 0);
+                if (force_cpl_d == 2 || (force_cpl_d == 0 && units2d >= 8 * n_sm)) {
+                    m1_scan_kernel<T, 2, false, false, false, true><<<units2d, 32, sizeof(ScanSmem<T, 2, true>), stream>>>(p, units2d);
+                } else {
+                    const int units1d = n_seq * (p.D / 32);
+                    m1_scan_kernel<T, 1, false, false, false, true><<<units1d, 32, sizeof(ScanSmem<T, 1, true>), stream>>>(p, units1d);
+                }
+                DM_CUDA_TRY(cudaGetLastError());
+                return DM_OK;
+            }
+        }
         if (save && gated) return DM_ERR_INVALID_ARG;                  // the backward needs the raw z
         if (save) {
             for (int g = 0; g < p.n_groups; ++g)
@@ -1158,6 +1210,8 @@ static int m1_dispatch(const dm_mamba1_args* a, int phases, void* stream) {
         d.conv_w = s.conv_weight; d.conv_b = s.conv_bias; d.wx = s.x_proj_weight; d.wdt = s.dt_proj_weight;
         d.dt_bias = s.dt_bias; d.A = s.A; d.D = s.D;
         d.chunk_states = s.chunk_states;
+        d.delta = static_cast<__half*>(s.delta);
+        if (s.delta != nullptr && !aligned16(s.delta)) return DM_ERR_INVALID_ARG;
         if (s.chunk_states != nullptr) p.save_every = dm_mamba1_bwd_chunk_tokens();
     }
     if (a->sched_workspace != nullptr && !aligned16(a->sched_workspace)) return DM_ERR_INVALID_ARG;

@@ -221,7 +221,7 @@ def _sched_workspace(device, batch: int, n_dir: int, d_inner: int, groups: int):
 
 
 def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, bufs=None, dynamic=None,
-                chunk_states=None, z_gated: bool = False):
+                chunk_states=None, z_gated: bool = False, delta=None):
     """Fill a ``dm_mamba1_args`` for the given groups.  Returns (args, (out, u, x_dbl)); the tensors own the memory
     the struct points at and must outlive the launch.  ``bufs`` = existing (out-shaped, u, x_dbl) tensors to point at
     instead of allocating (the backward passes dout / the saved intermediates)."""
@@ -271,6 +271,8 @@ def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: Scan
         gs.dt_bias = _ptr(_chk(w.dt_bias, torch.float32, (D,), "dt_bias"))
         gs.A = _chk(w.A, torch.float32, (D, N), "A").data_ptr()
         gs.D = _ptr(_chk(w.D, torch.float32, (D,), "D"))
+        if delta is not None:                   # (G, B, n_dir, seqlen, D) fp16: softplus'ed delta handed to the scan kernel
+            gs.delta = _chk(delta[g], torch.float16, (B, plan.n_dir, plan.seqlen, D), "delta").data_ptr()
         if chunk_states is not None:            # training: recurrence checkpoints for the backward (fp32, contiguous)
             gs.chunk_states = _chk(chunk_states[g], torch.float32, chunk_states.shape[1:], "chunk_states").data_ptr()
     return a, (out_all, u_all, xd_all)

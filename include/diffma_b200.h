@@ -86,6 +86,9 @@ typedef struct {
      * c = dm_mamba1_bwd_chunk_tokens(): (B, n_dir, ceil(seqlen/c), d_inner, d_state) fp32, contiguous.  Handed to
      * dm_mamba1_scan_bwd as `state_workspace` with `states_valid = 1` it saves the backward its forward sweep. */
     float* chunk_states;
+    /* optional, or NULL: (B, n_dir, seqlen, d_inner) fp16, contiguous, scan order: delta = softplus(dt_proj(dt_low) + bias).
+     * When given (bf16 activations), the scan kernel reads it instead of evaluating dt_proj + softplus itself. */
+    void* delta;
 } dm_mamba1_group;
 
 typedef struct {

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
 def test_struct_layouts_match_header_sizes():
     """ctypes mirrors of the argument structs: field counts / sizes as the C compiler lays them out."""
     from diffma_b200 import _cabi
-    assert ctypes.sizeof(_cabi.Mamba1Group) == 17 * 8            # + chunk_states (ABI 4)
+    assert ctypes.sizeof(_cabi.Mamba1Group) == 18 * 8            # + chunk_states (ABI 4), delta (ABI 5)
     assert ctypes.sizeof(_cabi.Mamba1Args) == 10 * 4 + 8 + 4 * ctypes.sizeof(_cabi.Mamba1Group) + 16 + 8   # + sched workspace ptr/size (ABI 3), z_is_gated (ABI 5)
     assert ctypes.sizeof(_cabi.GemmArgs) == 13 * 8 + 6 * 4                                              # 104 + 24 = 128
     assert ctypes.sizeof(_cabi.Mamba2Group) == 15 * 8

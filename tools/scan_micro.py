@@ -26,6 +26,8 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--phase", type=int, default=0)
 ap.add_argument("--fp32", action="store_true")
 ap.add_argument("--static", action="store_true", help="static schedule (no scheduler workspace)")
+ap.add_argument("--delta", action="store_true", help="experiment: hand the scan a precomputed fp16 delta (torch) instead of "
+                                                     "letting it run dt_proj + softplus")
 a_ = ap.parse_args()
 dev = torch.device("cuda:0")
 n = a_.side
@@ -47,6 +49,18 @@ lib, st = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 res = {}
 _cabi.check(lib.dm_mamba1_scan_phase(C.byref(a), 1, st), "phase 1")
+if a_.delta:
+    xd = keep[2]                                                    # (G, B, K, L, 64) fp32 rows [dt hi | dt lo | B | C]
+    hl = xd[..., :32].contiguous().view(torch.bfloat16).float()     # (..., 64): hi 32, lo 32
+    dt_low = hl[..., :32] + hl[..., 32:]
+    delta = torch.stack([torch.nn.functional.softplus(dt_low[g] @ w[g].dt_proj_weight.float().t() + w[g].dt_bias)
+                         for g in range(2)]).to(torch.float16).contiguous()
+    ref_out = None
+    _cabi.check(lib.dm_mamba1_scan_phase(C.byref(a), 2, st), "phase 2 (reference)")
+    ref_out = keep[0].float()
+if a_.delta:
+    res["delta_vs_inkernel_maxabs"] = float((out - ref_out).abs().max()).clone()
+    a, keep2 = ops.mamba1_args(xz, w, plan, dynamic=not a_.static, bufs=keep, delta=delta)
 for phase in ((1, 2) if a_.phase == 0 else (a_.phase,)):
     for _ in range(3):
         _cabi.check(lib.dm_mamba1_scan_phase(C.byref(a), phase, st), "phase")
@@ -63,6 +77,8 @@ for phase in ((1, 2) if a_.phase == 0 else (a_.phase,)):
     res[f"phase{phase}_us"] = round(ts[len(ts) // 2], 2)
     res[f"phase{phase}_min_us"] = round(ts[0], 2)
 out = keep[0].float()
+if a_.delta:
+    res["delta_vs_inkernel_maxabs"] = float((out - ref_out).abs().max())
 res.update(batch=B, L=L, schedule='static' if a_.static else 'dynamic', dtype=str(dt), out_sum=float(out.sum()), out_abs=float(out.abs().sum()),
            finite=bool(torch.isfinite(out).all()), env={k: v for k, v in os.environ.items() if k.startswith("DM_")})
 print(json.dumps(res))
