@@ -200,8 +200,9 @@ def kernel_roofline(args, device, peaks, batch=None, input_size=None, mamba2=Non
                                -torch.exp(torch.log(torch.arange(1, 17).float()).expand(D, 16)
                                           + 0.3 * torch.randn(D, 16, generator=g)).contiguous().to(device),
                                torch.ones(D, device=device)) for _ in range(2)]
-        # as the product path launches it: the in-projection's epilogue has already applied SiLU to z (z_is_gated)
-        a, keep = ops.mamba1_args(xz, w, plan, z_gated=True)
+        # as the product path launches it: kernel P hands delta = softplus(dt_proj(dt_low) + bias) to the scan as fp16
+        delta = torch.empty((2, B, 3, L, D), dtype=torch.float16, device=device) if ops.USE_DELTA_HANDOVER else None
+        a, keep = ops.mamba1_args(xz, w, plan, delta=delta)
         lib, st = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         for phase, name in ((1, "m1_conv_xproj_kernel"), (2, "m1_scan_kernel")):
             for _ in range(3):
@@ -215,12 +216,13 @@ def kernel_roofline(args, device, peaks, batch=None, input_size=None, mamba2=Non
             res[name] = sorted(e0.elapsed_time(e1) for e0, e1 in ev)[iters // 2] * 1e-3
         upstream = upstream_cuda_scan_us(2 * B * 3, D, L, device, flush) if with_upstream else None
         token_scans = 2 * B * 3 * L
-        # algorithmic bytes of the scan kernel per token-scan: read u, z (2*D*2 B) + x_dbl (64*4 B),
-        # write y*silu(z) (D*2 B)
-        bytes_per = 3 * D * 2 + 256
+        # algorithmic bytes of the scan kernel per token-scan: read u, z [, delta fp16] (D*2 B each) + x_dbl
+        # (64*4 B), write y*silu(z) (D*2 B)
+        bytes_per = (4 if delta is not None else 3) * D * 2 + 256
         dom, t = "m1_scan_kernel", res["m1_scan_kernel"]
-        exps = token_scans * D * 18           # 16 decays + softplus (2) MUFU ops per (token, channel); the gate's SiLU is
-        #                                       evaluated once per SOURCE token in the in-projection's epilogue
+        # MUFU ops of the SCAN kernel per (token, channel): 16 decays + the gate's tanh; with the delta hand-over the
+        # softplus (2 more) runs in kernel P, whose XU pipe is otherwise ~85 % idle
+        exps = token_scans * D * (17 if delta is not None else 19)
     else:
         upstream = None
         Cin = 2 * D + 32 + 16

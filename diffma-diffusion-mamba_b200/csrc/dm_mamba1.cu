@@ -290,6 +290,14 @@ __device__ __forceinline__ float silu_tanh(float x) {
     return fmaf(h, tanh_approx(h), h);
 }
 
+// softplus with torch's threshold on a log2(e)-scaled argument (same formula as the scan kernel's softplus_scaled)
+__device__ __forceinline__ float softplus_scaled_p(float s) {
+    float e, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(s));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+    return 0.6931471805599453f * (s > 28.853900817779268f ? s : l);
+}
+
 template <int kD>
 __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const __grid_constant__ M1P p, int n_tiles) {
     using T = __nv_bfloat16;
@@ -301,6 +309,9 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
     T* Ws = reinterpret_cast<T*>(smem_raw);                  // [64][ld]
     T* Xs = Ws + kE * ld;                                    // [2][kTP2 + 3][ld]
     int32_t* ord_s = reinterpret_cast<int32_t*>(Xs + 2 * tile_elems);   // [K][L] scan orders, loaded once per CTA
+    // dt_low tile (hi / lo bf16 halves) for the delta GEMM: [2][kTP2][kR + 8], 80-byte rows (ldmatrix conflict-free)
+    T* dtl = reinterpret_cast<T*>(ord_s + ((p.K * p.L + 3) & ~3));
+    constexpr int ldd = kR + 8;
     const int L = p.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_per_seq = (L + kTP2 - 1) / kTP2;
@@ -486,12 +497,61 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
                     split_bf16(s.x, s.y, hi, lo);
                     reinterpret_cast<uint32_t*>(rowp)[col / 2] = hi;
                     reinterpret_cast<uint32_t*>(rowp)[16 + col / 2] = lo;
+                    *reinterpret_cast<uint32_t*>(dtl + row * ldd + col) = hi;
+                    *reinterpret_cast<uint32_t*>(dtl + (kTP2 + row) * ldd + col) = lo;
                 } else {
                     *reinterpret_cast<float2*>(rowp + col) = s;
                 }
+            } else if (col < kR) {                          // rows past the end of the sequence: defined (zero) MMA operands
+                *reinterpret_cast<uint32_t*>(dtl + row * ldd + col) = 0u;
+                *reinterpret_cast<uint32_t*>(dtl + (kTP2 + row) * ldd + col) = 0u;
             }
         }
         __syncthreads();                                   // reduce buffer free before the next prefetch lands in it
+
+        // ---- delta tile (16 tokens x D) = softplus(dt_low (16 x 32) . W_dt^T + bias) -> fp16, for the scan kernel.
+        //      The scan is bound by the MUFU pipe and this kernel leaves it ~85 % idle: the 2 MUFU of the softplus per
+        //      (token, channel), the dt_proj MMA and its shared-memory round trip move here (scan 131 -> 109 us at the
+        //      headline shape, profiles/r02_notes.md).  Warp w owns channels [64 w, 64 w + 64); A = dt_low hi + lo from
+        //      shared memory (ldmatrix), B = W_dt rows straight from L2 / L1 (4 KB per warp and tile). ----
+        if (G.delta != nullptr) {
+            const T* Wdt = static_cast<const T*>(G.wdt) + static_cast<int64_t>(warp * 64 + (lane >> 2)) * kR + 2 * (lane & 3);
+            uint32_t bw[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const T* wp = Wdt + nt * 8 * kR;
+                bw[nt][0] = __ldg(reinterpret_cast<const uint32_t*>(wp));
+                bw[nt][1] = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
+                bw[nt][2] = __ldg(reinterpret_cast<const uint32_t*>(wp + 16));
+                bw[nt][3] = __ldg(reinterpret_cast<const uint32_t*>(wp + 24));
+            }
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                ldmatrix_x4(ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3],
+                            smem_u32(dtl + (lane & 15) * ldd + ks * 16 + (lane >> 4) * 8));
+                ldmatrix_x4(al[ks][0], al[ks][1], al[ks][2], al[ks][3],
+                            smem_u32(dtl + (kTP2 + (lane & 15)) * ldd + ks * 16 + (lane >> 4) * 8));
+            }
+            const int r0 = lane >> 2;
+            const bool ok0 = j0 + r0 < L, ok1 = j0 + r0 + 8 < L;
+            __half* drow = G.delta + (seq_in_group * L + j0 + r0) * kD + warp * 64 + 2 * (lane & 3);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_bf16_16816(dacc, ah[0], bw[nt][0], bw[nt][1]);
+                mma_bf16_16816(dacc, al[0], bw[nt][0], bw[nt][1]);
+                mma_bf16_16816(dacc, ah[1], bw[nt][2], bw[nt][3]);
+                mma_bf16_16816(dacc, al[1], bw[nt][2], bw[nt][3]);
+                float2 bb = make_float2(0.f, 0.f);
+                if (G.dt_bias) bb = __ldg(reinterpret_cast<const float2*>(G.dt_bias + warp * 64 + nt * 8 + 2 * (lane & 3)));
+                const float b0 = bb.x * kLog2e, b1 = bb.y * kLog2e;
+                const __half2 v0 = __floats2half2_rn(softplus_scaled_p(fmaf(dacc[0], kLog2e, b0)), softplus_scaled_p(fmaf(dacc[1], kLog2e, b1)));
+                const __half2 v1 = __floats2half2_rn(softplus_scaled_p(fmaf(dacc[2], kLog2e, b0)), softplus_scaled_p(fmaf(dacc[3], kLog2e, b1)));
+                if (ok0) *reinterpret_cast<__half2*>(drow + nt * 8) = v0;
+                if (ok1) *reinterpret_cast<__half2*>(drow + 8 * kD + nt * 8) = v1;
+            }
+        }
         cur = nxt;
     }
 }
@@ -1031,15 +1091,27 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
 }
 
 template <typename T>
-int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes) {
+int launch_m1(const M1P& p_in, int phases, cudaStream_t stream, size_t sched_bytes) {
+    M1P p = p_in;
     const int n_seq = p.n_groups * p.B * p.K;
     const bool split = sizeof(T) == 4;
     int dev = 0, n_sm = 0;
     if (int e = current_device(&dev, &n_sm); e != DM_OK) return e;
+    const size_t ld = static_cast<size_t>(p.D) + 8;
+    {   // delta is produced only by the persistent kernel P (bf16, d_inner 1024) and consumed only by the inference scan:
+        // anywhere else the scan evaluates dt_proj + softplus itself, whatever the caller passed
+        const size_t need = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2 + ((static_cast<size_t>(p.K) * p.L + 3) & ~size_t(3)) * 4 +
+                            2 * kTP2 * (kR + 8) * 2;
+        const bool persistent = !split && p.D == 1024 && need <= 227 * 1024;
+        bool all = persistent && p.save_every == 0 && p.z_gated == 0;
+        for (int g = 0; g < p.n_groups; ++g) all = all && p.g[g].delta != nullptr;
+        if (!all)
+            for (int g = 0; g < p.n_groups; ++g) p.g[g].delta = nullptr;
+    }
     // kernel P
     if (phases & 1) {
-        const size_t ld = static_cast<size_t>(p.D) + 8;
-        const size_t bytes2 = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2 + static_cast<size_t>(p.K) * p.L * 4;
+        const size_t bytes2 = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2 + ((static_cast<size_t>(p.K) * p.L + 3) & ~size_t(3)) * 4 +
+                              2 * kTP2 * (kR + 8) * 2;            // W_x + 2 x-tiles + scan orders + dt_low tile (hi, lo)
         if (!split && p.D == 1024 && bytes2 <= 227 * 1024) {                        // bf16, d_inner 1024: persistent kernel, W_x resident in shared memory
             static PerDeviceOnce cfg;
             if (!cfg.done(dev)) {
@@ -1105,24 +1177,14 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
         const bool gated = p.z_gated != 0;
         bool delta_in = !split;                   // delta handed over by kernel P (all groups or none; bf16 only)
         for (int g = 0; g < p.n_groups; ++g) delta_in = delta_in && p.g[g].delta != nullptr;
-        if (delta_in && !save && !gated) {
-            if constexpr (sizeof(T) == 2) {
-                static PerDeviceOnce dcfg;
-                if (!dcfg.done(dev)) {
-                    DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                    DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                    dcfg.set(dev);
-                }
-                const int units2d = n_seq * (p.D / 64);
-                static const int force_cpl_d = env_int("DM_SCAN_CPL", 0);
-                if (force_cpl_d == 2 || (force_cpl_d == 0 && units2d >= 8 * n_sm)) {
-                    m1_scan_kernel<T, 2, false, false, false, true><<<units2d, 32, sizeof(ScanSmem<T, 2, true>), stream>>>(p, units2d);
-                } else {
-                    const int units1d = n_seq * (p.D / 32);
-                    m1_scan_kernel<T, 1, false, false, false, true><<<units1d, 32, sizeof(ScanSmem<T, 1, true>), stream>>>(p, units1d);
-                }
-                DM_CUDA_TRY(cudaGetLastError());
-                return DM_OK;
+        delta_in = delta_in && !save && !gated;
+        if constexpr (sizeof(T) == 2) {
+            static PerDeviceOnce dcfg;
+            if (!dcfg.done(dev)) {
+                DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, false, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 2, true, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                DM_CUDA_TRY(cudaFuncSetAttribute(m1_scan_kernel<T, 1, false, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                dcfg.set(dev);
             }
         }
         if (save && gated) return DM_ERR_INVALID_ARG;                  // the backward needs the raw z
@@ -1156,16 +1218,39 @@ int launch_m1(const M1P& p, int phases, cudaStream_t stream, size_t sched_bytes)
                 q.n_segs = (n_chunks + q.seg_chunks - 1) / q.seg_chunks;
                 const long long items = static_cast<long long>(units2) * q.n_segs;
                 const int grid = items < slots ? static_cast<int>(items) : slots;
-                if (gated) m1_scan_kernel<T, 2, true, false, true><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
+                bool done = false;
+                if constexpr (sizeof(T) == 2) {
+                    if (delta_in) {
+                        m1_scan_kernel<T, 2, true, false, false, true><<<grid, 32, sizeof(ScanSmem<T, 2, true>), stream>>>(q, units2);
+                        done = true;
+                    }
+                }
+                if (done) {
+                } else if (gated) m1_scan_kernel<T, 2, true, false, true><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
                 else m1_scan_kernel<T, 2, true, false><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
-            } else if (gated) {
-                m1_scan_kernel<T, 2, false, false, true><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
             } else {
-                m1_scan_kernel<T, 2, false, false><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
+                bool done = false;
+                if constexpr (sizeof(T) == 2) {
+                    if (delta_in) {
+                        m1_scan_kernel<T, 2, false, false, false, true><<<units2, 32, sizeof(ScanSmem<T, 2, true>), stream>>>(p, units2);
+                        done = true;
+                    }
+                }
+                if (done) {
+                } else if (gated) m1_scan_kernel<T, 2, false, false, true><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
+                else m1_scan_kernel<T, 2, false, false><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
             }
         } else {
             const int units1 = n_seq * (p.D / 32);
-            if (gated) m1_scan_kernel<T, 1, false, false, true><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
+            bool done = false;
+            if constexpr (sizeof(T) == 2) {
+                if (delta_in) {
+                    m1_scan_kernel<T, 1, false, false, false, true><<<units1, 32, sizeof(ScanSmem<T, 1, true>), stream>>>(p, units1);
+                    done = true;
+                }
+            }
+            if (done) {
+            } else if (gated) m1_scan_kernel<T, 1, false, false, true><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
             else m1_scan_kernel<T, 1, false, false><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
         }
         DM_CUDA_TRY(cudaGetLastError());

@@ -198,6 +198,11 @@ def _strides(x: torch.Tensor):
 # for the life of the process (CUDA graphs hold its address); every launch leaves it re-armed (include/diffma_b200.h)
 _SCHED_WS = {}
 USE_DYNAMIC_SCHEDULE = True
+# kernel P hands the scan kernel delta = softplus(dt_proj(dt_low) + bias) as fp16 (inference, bf16, d_inner 1024): the
+# MUFU-bound scan sheds the softplus and the dt_proj MMA (131 -> 109 us at the headline shape).  DIFFMA_DELTA=0: the scan
+# evaluates them itself (round-1 behaviour; A/B runs).
+import os as _os
+USE_DELTA_HANDOVER = _os.environ.get("DIFFMA_DELTA", "1") != "0"
 
 
 def _sched_workspace(device, batch: int, n_dir: int, d_inner: int, groups: int):
@@ -291,7 +296,12 @@ def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: 
     xz[g]: (B, L_src, 2D) tokens-major (last-dim stride 1).  Returns (out, u, x_dbl), each with a leading group
     axis: ``out[g]`` has ``plan.out_shape``; u (scan order) and x_dbl are the intermediates the backward reads.
     """
-    a, bufs = mamba1_args(xz, weights, plan, chunk_states=chunk_states, z_gated=z_gated)
+    delta = None
+    x0 = xz[0]
+    if (USE_DELTA_HANDOVER and chunk_states is None and not z_gated and x0.dtype == torch.bfloat16
+            and x0.shape[-1] == 2048):
+        delta = torch.empty((len(xz), x0.shape[0], plan.n_dir, plan.seqlen, 1024), dtype=torch.float16, device=x0.device)
+    a, bufs = mamba1_args(xz, weights, plan, chunk_states=chunk_states, z_gated=z_gated, delta=delta)
     st = _cabi.lib().dm_mamba1_scan_fwd(C.byref(a), C.c_void_p(_stream_handle(xz[0].device)))
     _cabi.check(st, "dm_mamba1_scan_fwd")
     LAUNCH_COUNTER["kernels"] += 2

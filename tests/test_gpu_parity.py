@@ -262,6 +262,28 @@ def test_tcgen05_gemm_fused_producer_and_epilogues(dev, G, M, N, K, S):
     assert torch.equal(c2, c0)
 
 
+@pytest.mark.parametrize("B,side", [(2, 14), (16, 14), (20, 14)])
+def test_delta_handover_equals_in_kernel_dt_proj(dev, monkeypatch, B, side):
+    """Kernel P handing delta = softplus(dt_proj(dt_low) + bias) to the scan as fp16 (default for bf16 inference) vs the
+    scan evaluating dt_proj + softplus itself: one / two channels per lane and the ready-queue schedule (B = 2 / 16 / 20).
+    fp16 delta carries 11 mantissa bits (the reference's own bf16 delta carries 8): bf16-output tolerance."""
+    from diffma_b200 import ops, scan_orders
+    L = side * side
+    ml, _ = scan_orders.spiral(side)
+    xz, p = _m1_inputs(B, L, seed=40 + B)
+    xz_t = xz.transpose(1, 2).contiguous().bfloat16().to(dev)
+    w = ops.Mamba1Weights(p["conv_w"].reshape(1024, 4).to(dev), p["conv_b"].to(dev), p["x_proj"].bfloat16().to(dev),
+                          p["dt_proj"].bfloat16().to(dev), p["dt_bias"].to(dev), p["A"].to(dev), p["D"].to(dev))
+    plan = ops.ScanPlan.build([None, ml[2], ml[3]], L, "concat", dev)
+    outs = {}
+    for flag in (False, True):
+        monkeypatch.setattr(ops, "USE_DELTA_HANDOVER", flag)
+        o, u, xd = ops.mamba1_scan_raw([xz_t, xz_t.flip(0)], [w, w], plan)
+        outs[flag] = (o.float(), u, xd)
+    assert torch.equal(outs[True][1], outs[False][1]) and torch.equal(outs[True][2], outs[False][2])   # u, x_dbl untouched
+    torch.testing.assert_close(outs[True][0], outs[False][0], rtol=2e-2, atol=2e-2)
+
+
 def test_gated_scan_equals_scan_with_silu_inside(dev):
     """dm_mamba1_args.z_is_gated: feeding silu(z) (as the in-projection epilogue writes it) with the flag set gives the
     result of feeding z without it, up to the bf16 rounding of silu(z) -- both the 1- and the 2-channel-per-lane kernel."""

@@ -55,11 +55,9 @@ if a_.delta:
     dt_low = hl[..., :32] + hl[..., 32:]
     delta = torch.stack([torch.nn.functional.softplus(dt_low[g] @ w[g].dt_proj_weight.float().t() + w[g].dt_bias)
                          for g in range(2)]).to(torch.float16).contiguous()
-    ref_out = None
+    torch.cuda.synchronize()
     _cabi.check(lib.dm_mamba1_scan_phase(C.byref(a), 2, st), "phase 2 (reference)")
-    ref_out = keep[0].float()
-if a_.delta:
-    res["delta_vs_inkernel_maxabs"] = float((out - ref_out).abs().max()).clone()
+    ref_out = keep[0].float().clone()
     a, keep2 = ops.mamba1_args(xz, w, plan, dynamic=not a_.static, bufs=keep, delta=delta)
 for phase in ((1, 2) if a_.phase == 0 else (a_.phase,)):
     for _ in range(3):
