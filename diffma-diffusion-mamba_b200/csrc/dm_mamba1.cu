@@ -309,9 +309,6 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
     T* Ws = reinterpret_cast<T*>(smem_raw);                  // [64][ld]
     T* Xs = Ws + kE * ld;                                    // [2][kTP2 + 3][ld]
     int32_t* ord_s = reinterpret_cast<int32_t*>(Xs + 2 * tile_elems);   // [K][L] scan orders, loaded once per CTA
-    // dt_low tile (hi / lo bf16 halves) for the delta GEMM: [2][kTP2][kR + 8], 80-byte rows (ldmatrix conflict-free)
-    T* dtl = reinterpret_cast<T*>(ord_s + ((p.K * p.L + 3) & ~3));
-    constexpr int ldd = kR + 8;
     const int L = p.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_per_seq = (L + kTP2 - 1) / kTP2;
@@ -497,62 +494,88 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
                     split_bf16(s.x, s.y, hi, lo);
                     reinterpret_cast<uint32_t*>(rowp)[col / 2] = hi;
                     reinterpret_cast<uint32_t*>(rowp)[16 + col / 2] = lo;
-                    *reinterpret_cast<uint32_t*>(dtl + row * ldd + col) = hi;
-                    *reinterpret_cast<uint32_t*>(dtl + (kTP2 + row) * ldd + col) = lo;
                 } else {
                     *reinterpret_cast<float2*>(rowp + col) = s;
                 }
-            } else if (col < kR) {                          // rows past the end of the sequence: defined (zero) MMA operands
-                *reinterpret_cast<uint32_t*>(dtl + row * ldd + col) = 0u;
-                *reinterpret_cast<uint32_t*>(dtl + (kTP2 + row) * ldd + col) = 0u;
             }
         }
         __syncthreads();                                   // reduce buffer free before the next prefetch lands in it
 
-        // ---- delta tile (16 tokens x D) = softplus(dt_low (16 x 32) . W_dt^T + bias) -> fp16, for the scan kernel.
-        //      The scan is bound by the MUFU pipe and this kernel leaves it ~85 % idle: the 2 MUFU of the softplus per
-        //      (token, channel), the dt_proj MMA and its shared-memory round trip move here (scan 131 -> 109 us at the
-        //      headline shape, profiles/r02_notes.md).  Warp w owns channels [64 w, 64 w + 64); A = dt_low hi + lo from
-        //      shared memory (ldmatrix), B = W_dt rows straight from L2 / L1 (4 KB per warp and tile). ----
-        if (G.delta != nullptr) {
-            const T* Wdt = static_cast<const T*>(G.wdt) + static_cast<int64_t>(warp * 64 + (lane >> 2)) * kR + 2 * (lane & 3);
-            uint32_t bw[8][4];
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const T* wp = Wdt + nt * 8 * kR;
-                bw[nt][0] = __ldg(reinterpret_cast<const uint32_t*>(wp));
-                bw[nt][1] = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
-                bw[nt][2] = __ldg(reinterpret_cast<const uint32_t*>(wp + 16));
-                bw[nt][3] = __ldg(reinterpret_cast<const uint32_t*>(wp + 24));
-            }
-            uint32_t ah[2][4], al[2][4];
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                ldmatrix_x4(ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3],
-                            smem_u32(dtl + (lane & 15) * ldd + ks * 16 + (lane >> 4) * 8));
-                ldmatrix_x4(al[ks][0], al[ks][1], al[ks][2], al[ks][3],
-                            smem_u32(dtl + (kTP2 + (lane & 15)) * ldd + ks * 16 + (lane >> 4) * 8));
-            }
-            const int r0 = lane >> 2;
-            const bool ok0 = j0 + r0 < L, ok1 = j0 + r0 + 8 < L;
-            __half* drow = G.delta + (seq_in_group * L + j0 + r0) * kD + warp * 64 + 2 * (lane & 3);
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                float dacc[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_bf16_16816(dacc, ah[0], bw[nt][0], bw[nt][1]);
-                mma_bf16_16816(dacc, al[0], bw[nt][0], bw[nt][1]);
-                mma_bf16_16816(dacc, ah[1], bw[nt][2], bw[nt][3]);
-                mma_bf16_16816(dacc, al[1], bw[nt][2], bw[nt][3]);
-                float2 bb = make_float2(0.f, 0.f);
-                if (G.dt_bias) bb = __ldg(reinterpret_cast<const float2*>(G.dt_bias + warp * 64 + nt * 8 + 2 * (lane & 3)));
-                const float b0 = bb.x * kLog2e, b1 = bb.y * kLog2e;
-                const __half2 v0 = __floats2half2_rn(softplus_scaled_p(fmaf(dacc[0], kLog2e, b0)), softplus_scaled_p(fmaf(dacc[1], kLog2e, b1)));
-                const __half2 v1 = __floats2half2_rn(softplus_scaled_p(fmaf(dacc[2], kLog2e, b0)), softplus_scaled_p(fmaf(dacc[3], kLog2e, b1)));
-                if (ok0) *reinterpret_cast<__half2*>(drow + nt * 8) = v0;
-                if (ok1) *reinterpret_cast<__half2*>(drow + 8 * kD + nt * 8) = v1;
-            }
-        }
         cur = nxt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Kernel D (bf16 inference): delta = softplus(dt_low . W_dt^T + bias) -> fp16 (seq, L, D), handed to kernel S.
+//   The scan is bound by the MUFU pipe; the softplus (2 MUFU per (token, channel)), the dt_proj MMA and its
+//   shared-memory round trip cost it 131 -> 109 us at the headline shape, while as a stand-alone, fully parallel kernel
+//   they are HBM/XU-balanced and ~10 us (profiles/r02_notes.md; inside the persistent kernel P, whose phases are
+//   serialised by block barriers, the same work cost +30 us and was moved out again).
+//   One warp per (32 scanned tokens, 64 channels): A = dt_low hi + lo halves read straight from the x_dbl rows (the
+//   m16n8k16 A fragment is 4 words of a row), B = the W_dt rows of the warp's channels, both from L2 / L1.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kDTok = 32;
+__global__ void __launch_bounds__(128) m1_delta_kernel(const __grid_constant__ M1P p, int rows_per_group) {
+    using T = __nv_bfloat16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.D;
+    const int cblocks = D / 256;                                 // a CTA covers 256 channels (4 warps x 64)
+    const int tiles_per_group = (rows_per_group + kDTok - 1) / kDTok;
+    int t = blockIdx.x;
+    const int cb = t % cblocks; t /= cblocks;
+    const int tile = t % tiles_per_group, g = t / tiles_per_group;
+    const M1G& G = p.g[g];
+    const int row0 = tile * kDTok;                               // rows = (b, k, j) flattened: x_dbl and delta are contiguous
+    const int c0 = cb * 256 + warp * 64;
+    const int r = lane >> 2, q = lane & 3;
+    // B fragments: W_dt[c0 + 8 nt + r][16 ks + 2 q (+8)]
+    uint32_t bw[8][4];
+    const T* Wdt = static_cast<const T*>(G.wdt) + static_cast<int64_t>(c0 + r) * kR + 2 * q;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const T* wp = Wdt + nt * 8 * kR;
+        bw[nt][0] = __ldg(reinterpret_cast<const uint32_t*>(wp));
+        bw[nt][1] = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
+        bw[nt][2] = __ldg(reinterpret_cast<const uint32_t*>(wp + 16));
+        bw[nt][3] = __ldg(reinterpret_cast<const uint32_t*>(wp + 24));
+    }
+    float2 bias[8];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        bias[nt] = G.dt_bias ? __ldg(reinterpret_cast<const float2*>(G.dt_bias + c0 + nt * 8 + 2 * q)) : make_float2(0.f, 0.f);
+        bias[nt].x *= kLog2e; bias[nt].y *= kLog2e;
+    }
+#pragma unroll
+    for (int mt = 0; mt < kDTok / 16; ++mt) {
+        const int ra = row0 + mt * 16 + r, rb = ra + 8;
+        const bool oka = ra < rows_per_group, okb = rb < rows_per_group;
+        // x_dbl row as 32-bit words: [0,16) dt_low hi (bf16 pairs), [16,32) dt_low lo
+        const uint32_t* xa = reinterpret_cast<const uint32_t*>(G.x_dbl + static_cast<int64_t>(oka ? ra : 0) * kE);
+        const uint32_t* xb = reinterpret_cast<const uint32_t*>(G.x_dbl + static_cast<int64_t>(okb ? rb : 0) * kE);
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            ah[ks][0] = __ldg(xa + ks * 8 + q);      ah[ks][1] = __ldg(xb + ks * 8 + q);
+            ah[ks][2] = __ldg(xa + ks * 8 + 4 + q);  ah[ks][3] = __ldg(xb + ks * 8 + 4 + q);
+            al[ks][0] = __ldg(xa + 16 + ks * 8 + q);     al[ks][1] = __ldg(xb + 16 + ks * 8 + q);
+            al[ks][2] = __ldg(xa + 16 + ks * 8 + 4 + q); al[ks][3] = __ldg(xb + 16 + ks * 8 + 4 + q);
+        }
+        __half* da = G.delta + static_cast<int64_t>(ra) * D + c0 + 2 * q;
+        __half* db = G.delta + static_cast<int64_t>(rb) * D + c0 + 2 * q;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_bf16_16816(dacc, ah[0], bw[nt][0], bw[nt][1]);
+            mma_bf16_16816(dacc, al[0], bw[nt][0], bw[nt][1]);
+            mma_bf16_16816(dacc, ah[1], bw[nt][2], bw[nt][3]);
+            mma_bf16_16816(dacc, al[1], bw[nt][2], bw[nt][3]);
+            const __half2 v0 = __floats2half2_rn(softplus_scaled_p(fmaf(dacc[0], kLog2e, bias[nt].x)),
+                                                 softplus_scaled_p(fmaf(dacc[1], kLog2e, bias[nt].y)));
+            const __half2 v1 = __floats2half2_rn(softplus_scaled_p(fmaf(dacc[2], kLog2e, bias[nt].x)),
+                                                 softplus_scaled_p(fmaf(dacc[3], kLog2e, bias[nt].y)));
+            if (oka) *reinterpret_cast<__half2*>(da + nt * 8) = v0;
+            if (okb) *reinterpret_cast<__half2*>(db + nt * 8) = v1;
+        }
     }
 }
 
@@ -1098,20 +1121,16 @@ int launch_m1(const M1P& p_in, int phases, cudaStream_t stream, size_t sched_byt
     int dev = 0, n_sm = 0;
     if (int e = current_device(&dev, &n_sm); e != DM_OK) return e;
     const size_t ld = static_cast<size_t>(p.D) + 8;
-    {   // delta is produced only by the persistent kernel P (bf16, d_inner 1024) and consumed only by the inference scan:
+    {   // delta is produced (m1_delta_kernel, after kernel P) for bf16 activations and consumed only by the inference scan:
         // anywhere else the scan evaluates dt_proj + softplus itself, whatever the caller passed
-        const size_t need = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2 + ((static_cast<size_t>(p.K) * p.L + 3) & ~size_t(3)) * 4 +
-                            2 * kTP2 * (kR + 8) * 2;
-        const bool persistent = !split && p.D == 1024 && need <= 227 * 1024;
-        bool all = persistent && p.save_every == 0 && p.z_gated == 0;
+        bool all = !split && p.D % 256 == 0 && p.save_every == 0 && p.z_gated == 0;
         for (int g = 0; g < p.n_groups; ++g) all = all && p.g[g].delta != nullptr;
         if (!all)
             for (int g = 0; g < p.n_groups; ++g) p.g[g].delta = nullptr;
     }
     // kernel P
     if (phases & 1) {
-        const size_t bytes2 = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2 + ((static_cast<size_t>(p.K) * p.L + 3) & ~size_t(3)) * 4 +
-                              2 * kTP2 * (kR + 8) * 2;            // W_x + 2 x-tiles + scan orders + dt_low tile (hi, lo)
+        const size_t bytes2 = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2 + static_cast<size_t>(p.K) * p.L * 4;
         if (!split && p.D == 1024 && bytes2 <= 227 * 1024) {                        // bf16, d_inner 1024: persistent kernel, W_x resident in shared memory
             static PerDeviceOnce cfg;
             if (!cfg.done(dev)) {
@@ -1132,6 +1151,14 @@ int launch_m1(const M1P& p_in, int phases, cudaStream_t stream, size_t sched_byt
             m1_conv_xproj_kernel<T><<<n_seq * p.tiles_per_seq, kPThreads, bytes, stream>>>(p);
         }
         DM_CUDA_TRY(cudaGetLastError());
+        if constexpr (sizeof(T) == 2) {
+            if (p.g[0].delta != nullptr) {                       // (all groups or none: normalised above)
+                const int rows = p.B * p.K * p.L;
+                const int grid = p.n_groups * ((rows + kDTok - 1) / kDTok) * (p.D / 256);
+                m1_delta_kernel<<<grid, 128, 0, stream>>>(p, rows);
+                DM_CUDA_TRY(cudaGetLastError());
+            }
+        }
     }
     // kernel S
     if (phases & 2) {

@@ -198,9 +198,9 @@ def _strides(x: torch.Tensor):
 # for the life of the process (CUDA graphs hold its address); every launch leaves it re-armed (include/diffma_b200.h)
 _SCHED_WS = {}
 USE_DYNAMIC_SCHEDULE = True
-# kernel P hands the scan kernel delta = softplus(dt_proj(dt_low) + bias) as fp16 (inference, bf16, d_inner 1024): the
-# MUFU-bound scan sheds the softplus and the dt_proj MMA (131 -> 109 us at the headline shape).  DIFFMA_DELTA=0: the scan
-# evaluates them itself (round-1 behaviour; A/B runs).
+# A small kernel between conv + x_proj and the scan hands the scan delta = softplus(dt_proj(dt_low) + bias) as fp16
+# (inference, bf16, d_inner 1024): the MUFU-bound scan sheds the softplus and the dt_proj MMA (131 -> 109 us at the
+# headline shape).  DIFFMA_DELTA=0: the scan evaluates them itself (round-1 behaviour; A/B runs).
 import os as _os
 USE_DELTA_HANDOVER = _os.environ.get("DIFFMA_DELTA", "1") != "0"
 
@@ -304,7 +304,7 @@ def mamba1_scan_raw(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: 
     a, bufs = mamba1_args(xz, weights, plan, chunk_states=chunk_states, z_gated=z_gated, delta=delta)
     st = _cabi.lib().dm_mamba1_scan_fwd(C.byref(a), C.c_void_p(_stream_handle(xz[0].device)))
     _cabi.check(st, "dm_mamba1_scan_fwd")
-    LAUNCH_COUNTER["kernels"] += 2
+    LAUNCH_COUNTER["kernels"] += 3 if delta is not None else 2        # conv + x_proj, [delta,] scan
     return bufs
 
 

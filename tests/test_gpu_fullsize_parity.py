@@ -122,7 +122,7 @@ def test_benchmarked_scan_kernel_vs_oracle_and_cpl1(dev, B, side, variant):
     assert worst < 0.1
 
 
-def test_training_forward_checkpoint_variant_vs_oracle(dev):
+def test_training_forward_checkpoint_variant_vs_oracle(dev, monkeypatch):
     """C4 shape (XL/4: batch 32, L = 49, 2 mixers x 3 directions): ``m1_scan_kernel<bf16, 2, false, true>`` -- output vs
     the oracle, and the checkpoints it writes (state BEFORE every 4th token) vs the oracle's recurrence."""
     from diffma_b200 import ops
@@ -134,6 +134,7 @@ def test_training_forward_checkpoint_variant_vs_oracle(dev):
     w_dev = [_to_dev(ops, w, dev) for w in ws]
     states = torch.zeros(ops.mamba1_state_shape(2, B, plan, 1024, 16), dtype=torch.float32, device=dev)
     out, u, x_dbl = ops.mamba1_scan_raw(xz_dev, w_dev, plan, chunk_states=states)
+    monkeypatch.setattr(ops, "USE_DELTA_HANDOVER", False)       # same in-kernel dt_proj + softplus as the training variant
     plain, _, _ = ops.mamba1_scan_raw(xz_dev, w_dev, plan)
     torch.cuda.synchronize()
     assert torch.equal(out, plain), "the checkpointing variant must not change the output"
