@@ -514,10 +514,17 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
 //   One warp per (32 scanned tokens, 64 channels): A = dt_low hi + lo halves read straight from the x_dbl rows (the
 //   m16n8k16 A fragment is 4 words of a row), B = the W_dt rows of the warp's channels, both from L2 / L1.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kDTok = 32;
+constexpr int kDTok = 64;          // scanned tokens per warp: the W_dt fragments (32 registers) are loaded once per 64 x 64 tile
+struct DeltaSmem {                 // per warp; every row stride is an odd multiple of 16 B (ldmatrix / 16-byte accesses conflict free)
+    __nv_bfloat16 wd[64][kR + 8];  // the warp's W_dt rows
+    __nv_bfloat16 at[16][64 + 8];  // dt_low of 16 tokens: [hi 32 | lo 32]
+    __half stage[16][64 + 8];      // softplus'ed tile in fragment order -> row-order copy-out
+};
 __global__ void __launch_bounds__(128) m1_delta_kernel(const __grid_constant__ M1P p, int rows_per_group) {
     using T = __nv_bfloat16;
+    __shared__ __align__(16) DeltaSmem smem[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    DeltaSmem& S = smem[warp];
     const int D = p.D;
     const int cblocks = D / 256;                                 // a CTA covers 256 channels (4 warps x 64)
     const int tiles_per_group = (rows_per_group + kDTok - 1) / kDTok;
@@ -527,41 +534,54 @@ __global__ void __launch_bounds__(128) m1_delta_kernel(const __grid_constant__ M
     const M1G& G = p.g[g];
     const int row0 = tile * kDTok;                               // rows = (b, k, j) flattened: x_dbl and delta are contiguous
     const int c0 = cb * 256 + warp * 64;
-    const int r = lane >> 2, q = lane & 3;
-    // B fragments: W_dt[c0 + 8 nt + r][16 ks + 2 q (+8)]
-    uint32_t bw[8][4];
-    const T* Wdt = static_cast<const T*>(G.wdt) + static_cast<int64_t>(c0 + r) * kR + 2 * q;
+    const int q = lane & 3, r = lane >> 2;
+    // ---- W_dt rows c0 .. c0+63 (4 KB contiguous) -> shared, 16-byte coalesced; B fragments by ldmatrix ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const T*>(G.wdt) + static_cast<int64_t>(c0) * kR);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        const T* wp = Wdt + nt * 8 * kR;
-        bw[nt][0] = __ldg(reinterpret_cast<const uint32_t*>(wp));
-        bw[nt][1] = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
-        bw[nt][2] = __ldg(reinterpret_cast<const uint32_t*>(wp + 16));
-        bw[nt][3] = __ldg(reinterpret_cast<const uint32_t*>(wp + 24));
+        for (int i = 0; i < 8; ++i) {
+            const int v = lane + 32 * i;
+            *reinterpret_cast<uint4*>(&S.wd[v >> 2][(v & 3) * 8]) = __ldg(src + v);
+        }
     }
+    // A rows of a 16-token tile: the first 128 B of each x_dbl row, 4 x 16 B per lane (rows past the end: clamped)
+    auto fetch_a = [&](int mt, uint4 (&v)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = lane + 32 * i;
+            const int row = min(row0 + mt * 16 + (e >> 3), rows_per_group - 1);
+            v[i] = __ldg(reinterpret_cast<const uint4*>(G.x_dbl + static_cast<int64_t>(row) * kE) + (e & 7));
+        }
+    };
+    uint4 av[4];
+    fetch_a(0, av);
     float2 bias[8];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         bias[nt] = G.dt_bias ? __ldg(reinterpret_cast<const float2*>(G.dt_bias + c0 + nt * 8 + 2 * q)) : make_float2(0.f, 0.f);
         bias[nt].x *= kLog2e; bias[nt].y *= kLog2e;
     }
+    __syncwarp();
+    uint32_t bw[8][4];             // B fragments of k-steps 0 and 1 for the 8 channel tiles
 #pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+        ldmatrix_x4(bw[nt][0], bw[nt][1], bw[nt][2], bw[nt][3], smem_u32(&S.wd[nt * 8 + (lane & 7)][(lane >> 3) * 8]));
+#pragma unroll 1
     for (int mt = 0; mt < kDTok / 16; ++mt) {
-        const int ra = row0 + mt * 16 + r, rb = ra + 8;
-        const bool oka = ra < rows_per_group, okb = rb < rows_per_group;
-        // x_dbl row as 32-bit words: [0,16) dt_low hi (bf16 pairs), [16,32) dt_low lo
-        const uint32_t* xa = reinterpret_cast<const uint32_t*>(G.x_dbl + static_cast<int64_t>(oka ? ra : 0) * kE);
-        const uint32_t* xb = reinterpret_cast<const uint32_t*>(G.x_dbl + static_cast<int64_t>(okb ? rb : 0) * kE);
+        if (row0 + mt * 16 >= rows_per_group) break;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = lane + 32 * i;
+            *reinterpret_cast<uint4*>(&S.at[e >> 3][(e & 7) * 8]) = av[i];
+        }
+        __syncwarp();
+        if (mt + 1 < kDTok / 16) fetch_a(mt + 1, av);           // in flight while this tile is processed
         uint32_t ah[2][4], al[2][4];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            ah[ks][0] = __ldg(xa + ks * 8 + q);      ah[ks][1] = __ldg(xb + ks * 8 + q);
-            ah[ks][2] = __ldg(xa + ks * 8 + 4 + q);  ah[ks][3] = __ldg(xb + ks * 8 + 4 + q);
-            al[ks][0] = __ldg(xa + 16 + ks * 8 + q);     al[ks][1] = __ldg(xb + 16 + ks * 8 + q);
-            al[ks][2] = __ldg(xa + 16 + ks * 8 + 4 + q); al[ks][3] = __ldg(xb + 16 + ks * 8 + 4 + q);
+            ldmatrix_x4(ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], smem_u32(&S.at[lane & 15][ks * 16 + (lane >> 4) * 8]));
+            ldmatrix_x4(al[ks][0], al[ks][1], al[ks][2], al[ks][3], smem_u32(&S.at[lane & 15][32 + ks * 16 + (lane >> 4) * 8]));
         }
-        __half* da = G.delta + static_cast<int64_t>(ra) * D + c0 + 2 * q;
-        __half* db = G.delta + static_cast<int64_t>(rb) * D + c0 + 2 * q;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             float dacc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -569,13 +589,22 @@ __global__ void __launch_bounds__(128) m1_delta_kernel(const __grid_constant__ M
             mma_bf16_16816(dacc, al[0], bw[nt][0], bw[nt][1]);
             mma_bf16_16816(dacc, ah[1], bw[nt][2], bw[nt][3]);
             mma_bf16_16816(dacc, al[1], bw[nt][2], bw[nt][3]);
-            const __half2 v0 = __floats2half2_rn(softplus_scaled_p(fmaf(dacc[0], kLog2e, bias[nt].x)),
-                                                 softplus_scaled_p(fmaf(dacc[1], kLog2e, bias[nt].y)));
-            const __half2 v1 = __floats2half2_rn(softplus_scaled_p(fmaf(dacc[2], kLog2e, bias[nt].x)),
-                                                 softplus_scaled_p(fmaf(dacc[3], kLog2e, bias[nt].y)));
-            if (oka) *reinterpret_cast<__half2*>(da + nt * 8) = v0;
-            if (okb) *reinterpret_cast<__half2*>(db + nt * 8) = v1;
+            *reinterpret_cast<__half2*>(&S.stage[r][nt * 8 + 2 * q]) =
+                __floats2half2_rn(softplus_scaled_p(fmaf(dacc[0], kLog2e, bias[nt].x)), softplus_scaled_p(fmaf(dacc[1], kLog2e, bias[nt].y)));
+            *reinterpret_cast<__half2*>(&S.stage[r + 8][nt * 8 + 2 * q]) =
+                __floats2half2_rn(softplus_scaled_p(fmaf(dacc[2], kLog2e, bias[nt].x)), softplus_scaled_p(fmaf(dacc[3], kLog2e, bias[nt].y)));
         }
+        __syncwarp();
+        // row-order copy-out: 16 rows x 128 B = 128 16-byte vectors, 4 per lane, full 128-byte lines per 8 lanes
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int v = lane + 32 * i, rr = v >> 3, seg = v & 7;
+            const int row = row0 + mt * 16 + rr;
+            if (row < rows_per_group)
+                *reinterpret_cast<uint4*>(G.delta + static_cast<int64_t>(row) * D + c0 + seg * 8) =
+                    *reinterpret_cast<const uint4*>(&S.stage[rr][seg * 8]);
+        }
+        __syncwarp();                                           // stage / at are rewritten by the next tile
     }
 }
 

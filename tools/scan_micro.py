@@ -44,7 +44,10 @@ w = [ops.Mamba1Weights((torch.randn(D, 4, generator=g) * 0.4).to(dev), torch.zer
                        -torch.exp(torch.log(torch.arange(1, 17).float()).expand(D, 16)
                                   + 0.3 * torch.randn(D, 16, generator=g)).contiguous().to(dev),
                        torch.ones(D, device=dev)) for _ in range(2)]
-a, keep = ops.mamba1_args(xz, w, plan, dynamic=not a_.static)
+# product path (bf16): a small kernel after conv + x_proj hands delta = softplus(dt_proj + bias) to the scan as fp16
+use_delta = ops.USE_DELTA_HANDOVER and not a_.fp32 and not a_.delta
+delta0 = torch.empty((2, B, 3, L, D), dtype=torch.float16, device=dev) if use_delta else None
+a, keep = ops.mamba1_args(xz, w, plan, dynamic=not a_.static, delta=delta0)
 lib, st = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 res = {}
