@@ -718,6 +718,8 @@ __device__ __forceinline__ void ldmatrix_x4_u(uint32_t (&r)[4], uint32_t addr) {
                  : "r"(addr));
 }
 
+#include "dm_convx_tc.cuh"      // kernel P3 (tcgen05 conv + x_proj): needs the packed fp32x2 helpers above
+
 #ifdef DM_SCAN_TRACE
 // debugging aid (tools/scan_trace.py): per warp-unit {smid, warpid, start clock, end clock}
 __device__ unsigned long long g_scan_trace[4 * 8192];
@@ -1160,7 +1162,25 @@ int launch_m1(const M1P& p_in, int phases, cudaStream_t stream, size_t sched_byt
     // kernel P
     if (phases & 1) {
         const size_t bytes2 = (static_cast<size_t>(kE) + 2 * (kTP2 + 3)) * ld * 2 + static_cast<size_t>(p.K) * p.L * 4;
-        if (!split && p.D == 1024 && bytes2 <= 227 * 1024) {                        // bf16, d_inner 1024: persistent kernel, W_x resident in shared memory
+        // bf16, d_inner 1024: tensor-core kernel P3 (tcgen05, 128-token tiles; DM_CONVX=legacy selects the mma.sync
+        // persistent kernel below, which also serves shapes whose row offsets do not fit 32 bits)
+        static const int convx_legacy = [] { const char* e = getenv("DM_CONVX"); return (e && e[0] == 'l') ? 1 : 0; }();
+        bool use_tc = !split && p.D == 1024 && !convx_legacy && p.L >= 11;    // (>= 11 tokens: at most one sequence start per 8-row window)
+        for (int g = 0; g < p.n_groups && use_tc; ++g)
+            use_tc = static_cast<long long>(p.B) * p.g[g].xz_bs < (1ll << 31) && p.g[g].xz_ts % 8 == 0 && p.g[g].xz_bs % 8 == 0;
+        if (use_tc) {
+            if constexpr (sizeof(T) == 2) {
+                static PerDeviceOnce tcfg;
+                if (!tcfg.done(dev)) {
+                    DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, p3::kSmemBytes));
+                    tcfg.set(dev);
+                }
+                const int rows = p.B * p.K * p.L;
+                const int tiles_per_group = (rows + p3::kTile - 1) / p3::kTile;
+                const int n_tiles = tiles_per_group * p.n_groups;
+                m1_conv_xproj_tc<<<n_tiles < n_sm ? n_tiles : n_sm, p3::kThreads, p3::kSmemBytes, stream>>>(p, rows, tiles_per_group);
+            }
+        } else if (!split && p.D == 1024 && bytes2 <= 227 * 1024) {                 // persistent mma.sync kernel, W_x resident in shared memory
             static PerDeviceOnce cfg;
             if (!cfg.done(dev)) {
                 DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_persistent<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
