@@ -204,7 +204,8 @@ def kernel_roofline(args, device, peaks, batch=None, input_size=None, mamba2=Non
         delta = torch.empty((2, B, 3, L, D), dtype=torch.float16, device=device) if ops.USE_DELTA_HANDOVER else None
         a, keep = ops.mamba1_args(xz, w, plan, delta=delta)
         lib, st = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        for phase, name in ((1, "m1_conv_xproj_kernel"), (2, "m1_scan_kernel")):
+        # phase 1 = conv + x_proj (tcgen05 kernel P3) followed by the delta kernel; phase 2 = the scan
+        for phase, name in ((1, "m1_conv_xproj_tc+m1_delta_kernel" if delta is not None else "m1_conv_xproj"), (2, "m1_scan_kernel")):
             for _ in range(3):
                 _cabi.check(lib.dm_mamba1_scan_phase(C.byref(a), phase, st), "phase")
             for i in range(iters):
