@@ -641,25 +641,6 @@ template <typename T, int CPL> struct ScanSmem<T, CPL, true> {
     int rows[2][kCH];
 };
 
-// packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2): halves the issue slots of the recurrence
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 __device__ __forceinline__ float lg2_approx(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -672,11 +653,6 @@ __device__ __forceinline__ float lg2_approx(float x) {
 __device__ __forceinline__ float softplus_scaled(float s) {
     const float l = lg2_approx(1.0f + ex2_approx(s));
     return 0.6931471805599453f * (s > 28.853900817779268f ? s : l);
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
 }
 // 2^x for a packed pair of non-positive arguments on the FMA / ALU pipes instead of the MUFU: round-to-nearest split
 // x = n + f (magic-number add), degree-5 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 2.3e-7 in

@@ -72,11 +72,23 @@ __device__ __forceinline__ const int32_t* dir_order(const B1P& p, int k) {
     return (__ldg(o) < 0) ? nullptr : o;
 }
 
+constexpr int kXd = kE + 4;
+constexpr int kCk = kN + 4;
+constexpr int kTbhStride = 40;      // bf16 elements per channel row of the bf16 transposition matrix (80 bytes)
+constexpr int kTbStride = 34;   // float2 units per pair row of the transposition buffer: 2 * 34 words = 4 (mod 32), so
+                                // the eight lanes of a 128-bit load phase (pair rows p .. p + 7) cover all 32 banks
 template <typename T> struct BwdSmem {
-    float hs[kCH][kN][32];       // state BEFORE each token of the chunk
-    float xd[2][kCH][kE];        // x_dbl rows of the chunk, double buffered (cp.async)
-    float ds[kMR][34];           // delta_raw tile (the MMA tile has 8 token rows; rows >= kCH are never read)
-    float tb[32][33];            // transposition buffer for the dB / dC reduction over channels
+    uint64_t hs[kCH - 1][kN / 2][32];   // state BEFORE tokens 1 .. kCH-1 of the chunk, as packed pairs (n, n + 1)
+    float ck[2][32][kCk];        // state before token 0 = the chunk's checkpoint, staged by cp.async with the chunk's other
+                                 // inputs ([channel][16 states], 80-byte rows: 128-bit reads by lane are conflict free)
+    float xd[2][kCH][kXd];       // x_dbl rows of the chunk, double buffered (cp.async); 272-byte row stride: the four
+                                 // rows the dt_proj MMA gathers its A fragment from fall into different banks
+    float ds[kCH][40];           // delta_raw of the chunk's tokens (row stride 40 words: the MMA epilogue's 8-byte stores
+                                 // of rows 0..3 are conflict free)
+    // dB / dC reduction over the warp's 32 channels.  fp32 activations: [pair of values][channel] as packed fp32 pairs,
+    // summed by 128-bit row reads.  bf16 activations: the same memory holds a [channel][value] bf16 matrix (80-byte row
+    // stride) that ldmatrix.trans turns into the B operand of an all-ones MMA: half the shared-memory wavefronts.
+    uint64_t tb[sizeof(T) == 4 ? kN * kTbStride : 32 * kTbhStride / 4];
     T us[2][kCH][32], zs[2][kCH][32], dos[2][kCH][32];
 };
 
@@ -103,24 +115,31 @@ __global__ void __launch_bounds__(32, DM_BWD_MINB) m1_scan_bwd_kernel(const __gr
     float* hb = G.hb + ((sg * n_chunks) * D + c) * kN;                           // [chunk][D][16], this lane's channel
     const bool token_order = p.out_order == DM_OUT_TOKEN_ORDER;
 
-    float A2[kN];
+    uint64_t A2[kN / 2];                                                         // A * log2(e), pairs (n, n + 1)
 #pragma unroll
     for (int n = 0; n < kN; n += 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(G.A + static_cast<int64_t>(c) * kN + n));
-        A2[n] = t.x * kLog2e; A2[n + 1] = t.y * kLog2e; A2[n + 2] = t.z * kLog2e; A2[n + 3] = t.w * kLog2e;
+        A2[n / 2] = pack2(t.x * kLog2e, t.y * kLog2e);
+        A2[n / 2 + 1] = pack2(t.z * kLog2e, t.w * kLog2e);
     }
+    // decay pair a = 2^(dt * A2) on the MUFU
+    auto decay2 = [](uint64_t dt2, uint64_t a2) {
+        float e0, e1;
+        unpack2(mul2(dt2, a2), e0, e1);
+        return pack2(ex2_approx(e0), ex2_approx(e1));
+    };
     const float dtb = G.dt_bias ? __ldg(G.dt_bias + c) : 0.f;
     const float Dc = G.D ? __ldg(G.D + c) : 0.f;
 
-    // W_dt fragments (as in the forward kernel, 32 channels -> 4 n-tiles)
-    uint32_t bw_hi[4][2][2], bw_lo[4][2][2];
-    {
-        const T* Wdt = static_cast<const T*>(G.wdt);
+    // W_dt fragments (as in the forward kernel, 32 channels -> 4 n-tiles), held in registers for the whole sequence
+    // (re-fetching them per chunk to relieve the register allocator measured slower: 278 vs 270 us)
+    const T* Wdt = static_cast<const T*>(G.wdt) + static_cast<int64_t>(c0 + (lane >> 2)) * kR + 2 * (lane & 3);
+    auto load_w = [&](uint32_t (&bw_hi)[4][2][2], uint32_t (&bw_lo)[4][2][2]) {
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-                const T* wp = Wdt + static_cast<int64_t>(c0 + nt * 8 + (lane >> 2)) * kR + ks * 16 + 2 * (lane & 3);
+                const T* wp = Wdt + nt * 8 * kR + ks * 16;
                 if constexpr (kSplit) {
                     const float2 w0 = __ldg(reinterpret_cast<const float2*>(wp));
                     const float2 w1 = __ldg(reinterpret_cast<const float2*>(wp + 8));
@@ -131,7 +150,7 @@ __global__ void __launch_bounds__(32, DM_BWD_MINB) m1_scan_bwd_kernel(const __gr
                     bw_hi[nt][ks][1] = __ldg(reinterpret_cast<const uint32_t*>(wp + 8));
                 }
             }
-    }
+    };
 
     // Chunk staging, double buffered: issue() starts the cp.async copies of chunk ci (x_dbl rows, u, and for the reverse
     // sweep z and dout, 16-byte segments straight to shared memory) and returns at once; finish() waits for the OLDEST
@@ -145,14 +164,17 @@ __global__ void __launch_bounds__(32, DM_BWD_MINB) m1_scan_bwd_kernel(const __gr
     const T* do0 = do_base - lane;
     // source token of this lane's (row, segment) in the chunk the reverse sweep issues NEXT: read one chunk ahead, so
     // the scan-order lookup never sits between issue() and its dependent copies
-    int src_pref = 0;
-    auto load_src = [&](int ci) {
+    // (returned by value and handed to issue() as an argument: captured by reference it lived in local memory, and the
+    // store behind the load stalled every chunk on the lookup's latency)
+    auto load_src = [&](int ci) -> int {
+        int src = 0;
         if (ci >= 0 && lane < kCH * kSegRow) {
             const int j = min(ci * kCH + lane / kSegRow, L - 1);
-            src_pref = ord ? __ldg(ord + j) : j;
+            src = ord ? __ldg(ord + j) : j;
         }
+        return src;
     };
-    auto issue = [&](int ci, int buf, bool with_grad) {
+    auto issue = [&](int ci, int buf, bool with_grad, int src) {
         const int j0 = ci * kCH;
         for (int sgm = lane; sgm < kCH * (kE / 4); sgm += 32) {
             const int r = sgm / (kE / 4), part = sgm % (kE / 4);
@@ -164,16 +186,26 @@ __global__ void __launch_bounds__(32, DM_BWD_MINB) m1_scan_bwd_kernel(const __gr
             const int j = min(j0 + r, L - 1);
             cp_async16(smem_u32(&S.us[buf][r][part * kEpS]), u0 + static_cast<int64_t>(j) * D + part * kEpS);
             if (with_grad) {
-                const int src = src_pref;                     // kCH * kSegRow <= 32: this loop runs once per lane
+                // (kCH * kSegRow <= 32: this loop runs once per lane, src is this lane's row)
                 cp_async16(smem_u32(&S.zs[buf][r][part * kEpS]), z0 + static_cast<int64_t>(src) * G.xz_ts + part * kEpS);
                 cp_async16(smem_u32(&S.dos[buf][r][part * kEpS]),
                            do0 + static_cast<int64_t>(token_order ? src : j) * G.do_ts + part * kEpS);
             }
         }
+        if (with_grad) {
+            // the chunk's checkpoint: 32 channels x 16 states = 2 KB contiguous, 16-byte segments, coalesced
+            const float* ckg = G.hb + ((sg * n_chunks + ci) * D + c0) * kN;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = i * 32 + lane;
+                cp_async16(smem_u32(&S.ck[buf][idx >> 2][(idx & 3) * 4]), ckg + idx * 4);
+            }
+        }
         cp_async_commit();
-        if (with_grad) load_src(ci - 1);
     };
     static_assert(kCH * kSegRow <= 32, "one (row, segment) of u / z / dout per lane");
+    uint32_t bw_hi[4][2][2], bw_lo[4][2][2];
+    load_w(bw_hi, bw_lo);
     auto finish = [&](int buf, bool more_in_flight) {
         if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncwarp();
@@ -195,82 +227,103 @@ __global__ void __launch_bounds__(32, DM_BWD_MINB) m1_scan_bwd_kernel(const __gr
                 if constexpr (kSplit) mma_bf16_16816(dacc[nt], a_hi, bw_lo[nt][ks][0], bw_lo[nt][ks][1]);
             }
         }
+        if (r < kCH) {
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-            *reinterpret_cast<float2*>(&S.ds[r][nt * 8 + 2 * q]) = make_float2(dacc[nt][0], dacc[nt][1]);
+            for (int nt = 0; nt < 4; ++nt)
+                *reinterpret_cast<float2*>(&S.ds[r][nt * 8 + 2 * q]) = make_float2(dacc[nt][0], dacc[nt][1]);
+        }
         __syncwarp();
     };
 
     // ---- sweep 1: forward, boundary states -> workspace ----
-    float h[kN];
+    uint64_t h[kN / 2];
 #pragma unroll
-    for (int n = 0; n < kN; ++n) h[n] = 0.f;
+    for (int q = 0; q < kN / 2; ++q) h[q] = 0ull;
     // (skipped when the training forward already stored the checkpoints: G.states_valid)
-    if (n_chunks > 1 && !G.states_valid) issue(0, 0, false);
+    if (n_chunks > 1 && !G.states_valid) issue(0, 0, false, 0);
     for (int ci = 0; ci < n_chunks && !G.states_valid; ++ci) {
         float* hbc = hb + static_cast<int64_t>(ci) * D * kN;
 #pragma unroll
-        for (int n = 0; n < kN; n += 4) *reinterpret_cast<float4*>(hbc + n) = make_float4(h[n], h[n + 1], h[n + 2], h[n + 3]);
+        for (int q = 0; q < kN / 2; q += 2) *reinterpret_cast<ulonglong2*>(hbc + 2 * q) = make_ulonglong2(h[q], h[q + 1]);
         if (ci == n_chunks - 1) break;                       // the last chunk's end state is never needed
         const int buf = ci & 1;
         const bool more = ci + 1 < n_chunks - 1;             // sweep 1 visits chunks 0 .. n_chunks - 2
         __syncwarp();                                        // every lane is done with the buffer the prefetch overwrites
-        if (more) issue(ci + 1, buf ^ 1, false);
+        if (more) issue(ci + 1, buf ^ 1, false, 0);
         finish(buf, more);
 #pragma unroll
         for (int jj = 0; jj < kCH; ++jj) {
             const float dt = softplus_fast(S.ds[jj][lane] + dtb);
             const float dtu = dt * to_f32<T>(S.us[buf][jj][lane]);
-            const float* Bv = &S.xd[buf][jj][kR];
+            const uint64_t dt2 = pack2(dt, dt), dtu2 = pack2(dtu, dtu);
+            const ulonglong2* Bv = reinterpret_cast<const ulonglong2*>(&S.xd[buf][jj][kR]);
 #pragma unroll
-            for (int n = 0; n < kN; ++n) h[n] = fmaf(ex2_approx(dt * A2[n]), h[n], dtu * Bv[n]);
+            for (int q = 0; q < kN / 2; q += 2) {
+                const ulonglong2 b2 = Bv[q / 2];
+                h[q] = fma2(decay2(dt2, A2[q]), h[q], mul2(dtu2, b2.x));
+                h[q + 1] = fma2(decay2(dt2, A2[q + 1]), h[q + 1], mul2(dtu2, b2.y));
+            }
         }
     }
 
     // ---- sweep 2: reverse ----
-    float dh[kN], dA[kN];
+    if (!G.states_valid) __threadfence_block();                // sweep 1's checkpoints are re-read through cp.async below
+    // All the per-state arithmetic runs on packed pairs (fma / mul .f32x2): the kernel was bound by instruction issue and
+    // the shared-memory pipe together (r02 ncu: 627 warp instructions and 153 shared wavefronts per token, issue 62 %,
+    // LSU wavefronts 69 %), and 52 % of those instructions were scalar FMUL / FFMA / FADD of this loop.
+    uint64_t dh[kN / 2], dA[kN / 2];
 #pragma unroll
-    for (int n = 0; n < kN; ++n) { dh[n] = 0.f; dA[n] = 0.f; }
+    for (int q = 0; q < kN / 2; ++q) { dh[q] = 0ull; dA[q] = 0ull; }
     float dD = 0.f, ddtb = 0.f;
     float* dz_out = G.d_xz_scan + sg * L * 2 * D + D + c;
     float* du_out = G.du + sg * L * D + c;
     float* dd_out = G.ddelta + sg * L * D + c;
     float* dxd_out = G.d_x_dbl + sg * L * kE;
+    // reduction roles: lane (pr, half) sums pair row pr of the transposition buffer over channels half * 16 .. + 15,
+    // then the two halves swap one component: the lane ends with value 2 * pr + half (0..15 = dB, 16..31 = dC)
+    const int pr = lane & 15, half = lane >> 4;
     __syncwarp();
-    load_src(n_chunks - 1);
-    issue(n_chunks - 1, (n_chunks - 1) & 1, true);
+    issue(n_chunks - 1, (n_chunks - 1) & 1, true, load_src(n_chunks - 1));
+    int src_next = load_src(n_chunks - 2);
     for (int ci = n_chunks - 1; ci >= 0; --ci) {
         const int j0 = ci * kCH, nrows = min(kCH, L - j0);
         const int buf = ci & 1;
         __syncwarp();                                        // every lane is done with the buffer the prefetch overwrites
-        if (ci > 0) issue(ci - 1, buf ^ 1, true);
-        finish(buf, ci > 0);
-        const float* hbc = hb + static_cast<int64_t>(ci) * D * kN;
-#pragma unroll
-        for (int n = 0; n < kN; n += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(hbc + n);
-            h[n] = t.x; h[n + 1] = t.y; h[n + 2] = t.z; h[n + 3] = t.w;
+        if (ci > 0) {
+            issue(ci - 1, buf ^ 1, true, src_next);
+            src_next = load_src(ci - 2);
         }
-        float dtv[kCH], yv[kCH];
-        // forward through the chunk: keep the state before each token in shared memory, y in registers
+        finish(buf, ci > 0);
+        const ulonglong2* ckl = reinterpret_cast<const ulonglong2*>(&S.ck[buf][lane][0]);
+#pragma unroll
+        for (int q = 0; q < kN / 2; q += 2) {
+            const ulonglong2 t = ckl[q / 2];
+            h[q] = t.x; h[q + 1] = t.y;
+        }
+        float dtv[kCH];
+        // forward through the chunk: keep the state before each token in shared memory (y is rebuilt by the adjoint pass
+        // from the state after the token, which it holds anyway: one broadcast read of C per token instead of two)
 #pragma unroll
         for (int jj = 0; jj < kCH; ++jj) {
             const float dt = softplus_fast(S.ds[jj][lane] + dtb);
             const float uu = to_f32<T>(S.us[buf][jj][lane]);
             const float dtu = dt * uu;
-            const float* Bv = &S.xd[buf][jj][kR];
-            const float* Cv = &S.xd[buf][jj][kR + kN];
-            float y = 0.f;
+            const uint64_t dt2 = pack2(dt, dt), dtu2 = pack2(dtu, dtu);
+            const ulonglong2* Bv = reinterpret_cast<const ulonglong2*>(&S.xd[buf][jj][kR]);
 #pragma unroll
-            for (int n = 0; n < kN; ++n) {
-                S.hs[jj][n][lane] = h[n];
-                h[n] = fmaf(ex2_approx(dt * A2[n]), h[n], dtu * Bv[n]);
-                y = fmaf(h[n], Cv[n], y);
+            for (int q = 0; q < kN / 2; q += 2) {
+                const ulonglong2 b2 = Bv[q / 2];
+                if (jj > 0) {
+                    S.hs[jj - 1][q][lane] = h[q];
+                    S.hs[jj - 1][q + 1][lane] = h[q + 1];
+                }
+                h[q] = fma2(decay2(dt2, A2[q]), h[q], mul2(dtu2, b2.x));
+                h[q + 1] = fma2(decay2(dt2, A2[q + 1]), h[q + 1], mul2(dtu2, b2.y));
             }
             dtv[jj] = dt;
-            yv[jj] = fmaf(Dc, uu, y);
         }
-        // adjoint recurrence, last token of the chunk first
+        // adjoint recurrence, last token of the chunk first.  h = state AFTER the token being processed: the chunk's end
+        // state first, then the "state before" of the token handled one iteration earlier.
 #pragma unroll
         for (int jj = kCH - 1; jj >= 0; --jj) {
             if (jj < nrows) {
@@ -281,47 +334,123 @@ __global__ void __launch_bounds__(32, DM_BWD_MINB) m1_scan_bwd_kernel(const __gr
                 const float go = to_f32<T>(S.dos[buf][jj][lane]);
                 const float sg_z = sigmoid_fast(zz);
                 const float dy = go * zz * sg_z;                                   // d out / d y = silu(z)
-                const float dz = go * yv[jj] * sg_z * fmaf(zz, 1.0f - sg_z, 1.0f);    // silu'(z) = s (1 + z (1 - s))
                 dD = fmaf(dy, uu, dD);
-                const float* Bv = &S.xd[buf][jj][kR];
-                const float* Cv = &S.xd[buf][jj][kR + kN];
-                float ddt = 0.f, dbu = 0.f;     // d delta, sum_n dh_n B_n
-                float pB[kN], pC[kN];
+                const float w = dt * uu;
+                const uint64_t dt2 = pack2(dt, dt), dy2 = pack2(dy, dy), w2 = pack2(w, w);
+                const ulonglong2* Bv = reinterpret_cast<const ulonglong2*>(&S.xd[buf][jj][kR]);
+                const ulonglong2* Cv = reinterpret_cast<const ulonglong2*>(&S.xd[buf][jj][kR + kN]);
+                uint64_t ddt2 = 0ull, dbu2 = 0ull, y2 = 0ull;   // d delta (before the ln2 scale), sum_n dh_n B_n, y
+                uint32_t pw[kSplit ? 1 : kN];          // bf16 path: this channel's row of the [channel][value] matrix
+                __syncwarp();                          // the previous token's reduction has read the buffer
 #pragma unroll
-                for (int n = 0; n < kN; ++n) {
-                    const float hp = S.hs[jj][n][lane];
-                    const float a = ex2_approx(dt * A2[n]);
-                    const float hcur = fmaf(a, hp, dt * uu * Bv[n]);               // state after token jj
-                    pC[n] = dy * hcur;                                              // dC_j[n] contribution of this channel
-                    dh[n] = fmaf(dy, Cv[n], dh[n]);                                 // dL/dh_j
-                    const float t = dh[n] * hp * a;
-                    dA[n] = fmaf(t, dt, dA[n]);                                     // d/dA: dh * hp * a * dt
-                    ddt = fmaf(t, A2[n], ddt);                                      // (scaled by ln2 below) dh * hp * a * A
-                    dbu = fmaf(dh[n], Bv[n], dbu);
-                    pB[n] = dh[n] * dt * uu;                                        // dB_j[n] contribution
-                    dh[n] *= a;                                                     // -> dL/dh_{j-1} through the decay
+                for (int q = 0; q < kN / 2; q += 2) {
+                    const ulonglong2 bq = Bv[q / 2], cq = Cv[q / 2];
+                    ulonglong2 hq;                                                  // state before the token, pairs q, q + 1
+                    if (jj > 0) hq = make_ulonglong2(S.hs[jj - 1][q][lane], S.hs[jj - 1][q + 1][lane]);
+                    else hq = ckl[q / 2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const uint64_t b2 = e ? bq.y : bq.x, c2 = e ? cq.y : cq.x;
+                        const int qq = q + e;
+                        const uint64_t hp = e ? hq.y : hq.x;
+                        const uint64_t a = decay2(dt2, A2[qq]);
+                        y2 = fma2(h[qq], c2, y2);
+                        const uint64_t pc = mul2(dy2, h[qq]);                       // dC_j contribution of this channel
+                        dh[qq] = fma2(dy2, c2, dh[qq]);                             // dL/dh_j
+                        dbu2 = fma2(dh[qq], b2, dbu2);
+                        const uint64_t pb = mul2(dh[qq], w2);                       // dB_j contribution
+                        if constexpr (kSplit) {
+                            S.tb[(kN / 2 + qq) * kTbStride + lane] = pc;
+                            S.tb[qq * kTbStride + lane] = pb;
+                        } else {
+                            float x0, x1;
+                            unpack2(pb, x0, x1);
+                            pw[qq] = pack_bf16(x0, x1);
+                            unpack2(pc, x0, x1);
+                            pw[kN / 2 + qq] = pack_bf16(x0, x1);
+                        }
+                        dh[qq] = mul2(dh[qq], a);                                   // -> dL/dh_{j-1} through the decay
+                        const uint64_t t = mul2(dh[qq], hp);                        // dh_j * a * h_{j-1}
+                        dA[qq] = fma2(t, dt2, dA[qq]);
+                        ddt2 = fma2(t, A2[qq], ddt2);                               // (scaled by ln2 below)
+                        h[qq] = hp;
+                    }
+                    if constexpr (!kSplit) {
+                        if ((q & 2) != 0) {            // four pairs of dB and of dC are complete: two 16-byte row segments
+                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(&S.tb[0]) + lane * kTbhStride);
+                            const int i = q >> 2;
+                            dst[i] = make_uint4(pw[4 * i], pw[4 * i + 1], pw[4 * i + 2], pw[4 * i + 3]);
+                            dst[2 + i] = make_uint4(pw[8 + 4 * i], pw[9 + 4 * i], pw[10 + 4 * i], pw[11 + 4 * i]);
+                        }
+                    }
                 }
-                ddt = fmaf(ddt, 0.6931471805599453f, dbu * uu);
+                float s0, s1, t0, t1, ya, yb;
+                unpack2(ddt2, s0, s1);
+                unpack2(dbu2, t0, t1);
+                unpack2(y2, ya, yb);
+                const float dz = go * fmaf(Dc, uu, ya + yb) * sg_z * fmaf(zz, 1.0f - sg_z, 1.0f);   // silu'(z) = s (1 + z (1 - s))
+                const float dbu = t0 + t1;
+                const float ddt = fmaf(s0 + s1, 0.6931471805599453f, dbu * uu);
                 const float du = fmaf(dy, Dc, dbu * dt);
                 const float ddr = ddt * sigmoid_fast(S.ds[jj][lane] + dtb);          // softplus'(x) = sigmoid(x)
                 ddtb += ddr;
                 dz_out[static_cast<int64_t>(j) * 2 * D] = dz;
                 du_out[static_cast<int64_t>(j) * D] = du;
                 dd_out[static_cast<int64_t>(j) * D] = ddr;
-                // reduce dB / dC over the warp's 32 channels: transpose through shared memory, lane v sums value v
-                __syncwarp();
+                // reduce dB / dC over the warp's 32 channels
+                if constexpr (kSplit) {
+                    __syncwarp();
+                    const ulonglong2* trow = reinterpret_cast<const ulonglong2*>(&S.tb[pr * kTbStride + half * 16]);
+                    uint64_t r0 = 0ull, r1 = 0ull;
 #pragma unroll
-                for (int n = 0; n < kN; ++n) { S.tb[n][lane] = pB[n]; S.tb[kN + n][lane] = pC[n]; }
-                __syncwarp();
-                float s = 0.f;
+                    for (int i = 0; i < 8; ++i) {
+                        const ulonglong2 v = trow[i];
+                        r0 = add2(r0, v.x);
+                        r1 = add2(r1, v.y);
+                    }
+                    float lo, hi;
+                    unpack2(add2(r0, r1), lo, hi);
+                    const float mine = half ? hi : lo, other = half ? lo : hi;
+                    const float s = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+                    atomicAdd(dxd_out + static_cast<int64_t>(j) * kE + kR + 2 * pr + half, s);
+                } else {
+                    // column sums of the [32 channels][32 values] bf16 matrix = ones[16 x 32] . M on the tensor core: the
+                    // terms are rounded to bf16 (the activations they are built from already are), the sum is fp32
+                    __nv_bfloat16* tbh = reinterpret_cast<__nv_bfloat16*>(&S.tb[0]);
+                    __syncwarp();
+                    const uint32_t ones[4] = {0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u};
+                    float acc[4][4];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) s += S.tb[lane][i];
-                atomicAdd(dxd_out + static_cast<int64_t>(j) * kE + kR + lane, s);
+                    for (int t = 0; t < 4; ++t) {
+                        uint32_t b0, b1, b2, b3;       // k = channels 0-7, 8-15, 16-23, 24-31 of value columns 8t .. 8t+7
+                        ldmatrix_x4_trans(b0, b1, b2, b3, smem_u32(tbh + lane * kTbhStride + 8 * t));
+                        acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+                        mma_bf16_16816(acc[t], ones, b0, b1);
+                        mma_bf16_16816(acc[t], ones, b2, b3);
+                    }
+                    // every row of the product is the same: lane (row r, quad q) adds value 8 (r & 3) + 2 q + (r >> 2)
+                    const int r = lane >> 2, q = lane & 3, e = (r >> 2) & 1, t = r & 3;
+                    const float v0 = e ? acc[0][1] : acc[0][0], v1 = e ? acc[1][1] : acc[1][0];
+                    const float v2 = e ? acc[2][1] : acc[2][0], v3 = e ? acc[3][1] : acc[3][0];
+                    const float s = (t & 2) ? ((t & 1) ? v3 : v2) : ((t & 1) ? v1 : v0);
+                    atomicAdd(dxd_out + static_cast<int64_t>(j) * kE + kR + 8 * t + 2 * q + e, s);
+                }
+            } else {
+                if (jj > 0) {                                                        // tail chunk (jj >= nrows >= 1)
+#pragma unroll
+                    for (int q = 0; q < kN / 2; ++q) h[q] = S.hs[jj - 1][q][lane];  // state after token jj - 1
+                }
             }
         }
     }
+    float* dAo = G.dA + static_cast<int64_t>(c) * kN;
 #pragma unroll
-    for (int n = 0; n < kN; ++n) atomicAdd(G.dA + static_cast<int64_t>(c) * kN + n, dA[n]);
+    for (int q = 0; q < kN / 2; ++q) {
+        float x0, x1;
+        unpack2(dA[q], x0, x1);
+        atomicAdd(dAo + 2 * q, x0);
+        atomicAdd(dAo + 2 * q + 1, x1);
+    }
     if (G.dD) atomicAdd(G.dD + c, dD);
     if (G.d_dt_bias) atomicAdd(G.d_dt_bias + c, ddtb);
 }
