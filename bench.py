@@ -221,9 +221,10 @@ def kernel_roofline(args, device, peaks, batch=None, input_size=None, mamba2=Non
         # (64*4 B), write y*silu(z) (D*2 B)
         bytes_per = (4 if delta is not None else 3) * D * 2 + 256
         dom, t = "m1_scan_kernel", res["m1_scan_kernel"]
-        # MUFU ops of the SCAN kernel per (token, channel): 16 decays + the gate's tanh; with the delta hand-over the
-        # softplus (2 more) runs in kernel P, whose XU pipe is otherwise ~85 % idle
-        exps = token_scans * D * (17 if delta is not None else 19)
+        # MUFU ops of the SCAN kernel per (token, channel): 14 of the 16 decays (one state pair is evaluated by a
+        # polynomial on the FMA pipe, DM_POLY_PAIRS = 1 in csrc/dm_mamba1.cu) + the gate's tanh; with the delta hand-over
+        # the softplus (2 more) runs in m1_delta_kernel
+        exps = token_scans * D * (15 if delta is not None else 17)
     else:
         upstream = None
         Cin = 2 * D + 32 + 16

@@ -62,6 +62,7 @@ spiral_pre_kernel(const float* __restrict__ x, const float* __restrict__ skip, c
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
+    pdl_wait();                                 // (PDL: the predecessor's writes are visible from here on)
     const int b = row / L;
     float v[NV][8];
     float s = 0.f;
@@ -119,6 +120,7 @@ spiral_post_ln_kernel(const T* __restrict__ ab, const float* __restrict__ ln_w, 
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
+    pdl_wait();                                 // (PDL: the predecessor's writes are visible from here on)
     float v[2][NV][8];
     float s = 0.f;
 #pragma unroll
@@ -164,6 +166,7 @@ spiral_post_mix_kernel(const float* __restrict__ x, const float* __restrict__ sk
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
+    pdl_wait();                                 // (PDL: the predecessor's writes are visible from here on)
     const int b = row / L;
     float s = 0.f;
 #pragma unroll
@@ -213,6 +216,7 @@ spiral_post_mix_pre_kernel(const float* __restrict__ x, const float* __restrict_
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
+    pdl_wait();                                 // (PDL: the predecessor's writes are visible from here on)
     const int b = row / L;
     float s = 0.f;
 #pragma unroll
@@ -304,11 +308,9 @@ extern "C" int dm_spiral_pre(const float* x, const float* skip, const float* ln_
     const int rows = batch * seqlen;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (act_dtype == DM_BF16)
-        spiral_pre_kernel<__nv_bfloat16, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
-            x, skip, ln_weight, ln_bias, mod, mod_batch_stride, w, static_cast<__nv_bfloat16*>(out2), rows, seqlen, eps);
+        launch_pdl(kPdlRow, spiral_pre_kernel<__nv_bfloat16, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, x, skip, ln_weight, ln_bias, mod, mod_batch_stride, w, static_cast<__nv_bfloat16*>(out2), rows, seqlen, eps);
     else if (act_dtype == DM_F32)
-        spiral_pre_kernel<float, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
-            x, skip, ln_weight, ln_bias, mod, mod_batch_stride, w, static_cast<float*>(out2), rows, seqlen, eps);
+        launch_pdl(kPdlRow, spiral_pre_kernel<float, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, x, skip, ln_weight, ln_bias, mod, mod_batch_stride, w, static_cast<float*>(out2), rows, seqlen, eps);
     else
         return DM_ERR_UNSUPPORTED;
     DM_CUDA_TRY(cudaGetLastError());
@@ -322,11 +324,9 @@ extern "C" int dm_spiral_post_ln(const void* ab, const float* ln_weight, const f
     if (!aligned16(ab) || !aligned16(out)) return DM_ERR_INVALID_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (act_dtype == DM_BF16)
-        spiral_post_ln_kernel<__nv_bfloat16, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(ab), ln_weight, ln_bias, static_cast<__nv_bfloat16*>(out), rows, eps);
+        launch_pdl(kPdlRow, spiral_post_ln_kernel<__nv_bfloat16, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, static_cast<const __nv_bfloat16*>(ab), ln_weight, ln_bias, static_cast<__nv_bfloat16*>(out), rows, eps);
     else if (act_dtype == DM_F32)
-        spiral_post_ln_kernel<float, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
-            static_cast<const float*>(ab), ln_weight, ln_bias, static_cast<float*>(out), rows, eps);
+        launch_pdl(kPdlRow, spiral_post_ln_kernel<float, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, static_cast<const float*>(ab), ln_weight, ln_bias, static_cast<float*>(out), rows, eps);
     else
         return DM_ERR_UNSUPPORTED;
     DM_CUDA_TRY(cudaGetLastError());
@@ -344,12 +344,10 @@ extern "C" int dm_spiral_post_mix(const float* x, const float* skip, const void*
     const int rows = batch * seqlen;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (act_dtype == DM_BF16)
-        spiral_post_mix_kernel<__nv_bfloat16, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
-            x, skip, static_cast<const __nv_bfloat16*>(ab), static_cast<const __nv_bfloat16*>(hidden), w3, b3, mod,
+        launch_pdl(kPdlRow, spiral_post_mix_kernel<__nv_bfloat16, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, x, skip, static_cast<const __nv_bfloat16*>(ab), static_cast<const __nv_bfloat16*>(hidden), w3, b3, mod,
             mod_batch_stride, out, rows, seqlen);
     else if (act_dtype == DM_F32)
-        spiral_post_mix_kernel<float, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
-            x, skip, static_cast<const float*>(ab), static_cast<const float*>(hidden), w3, b3, mod, mod_batch_stride,
+        launch_pdl(kPdlRow, spiral_post_mix_kernel<float, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, x, skip, static_cast<const float*>(ab), static_cast<const float*>(hidden), w3, b3, mod, mod_batch_stride,
             out, rows, seqlen);
     else
         return DM_ERR_UNSUPPORTED;
@@ -375,13 +373,11 @@ extern "C" int dm_spiral_post_mix_pre(const float* x, const float* skip, const v
     const int rows = batch * seqlen;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (act_dtype == DM_BF16)
-        spiral_post_mix_pre_kernel<__nv_bfloat16, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
-            x, skip, static_cast<const __nv_bfloat16*>(ab), static_cast<const __nv_bfloat16*>(hidden), w3, b3, mod,
+        launch_pdl(kPdlRow, spiral_post_mix_pre_kernel<__nv_bfloat16, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, x, skip, static_cast<const __nv_bfloat16*>(ab), static_cast<const __nv_bfloat16*>(hidden), w3, b3, mod,
             mod_batch_stride, x_out, skip_next, ln_weight, ln_bias, mod_next, mod_next_batch_stride, w,
             static_cast<__nv_bfloat16*>(out2), rows, seqlen, eps);
     else if (act_dtype == DM_F32)
-        spiral_post_mix_pre_kernel<float, 2><<<row_grid(rows), kRowWarps * 32, 0, st>>>(
-            x, skip, static_cast<const float*>(ab), static_cast<const float*>(hidden), w3, b3, mod, mod_batch_stride, x_out,
+        launch_pdl(kPdlRow, spiral_post_mix_pre_kernel<float, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, x, skip, static_cast<const float*>(ab), static_cast<const float*>(hidden), w3, b3, mod, mod_batch_stride, x_out,
             skip_next, ln_weight, ln_bias, mod_next, mod_next_batch_stride, w, static_cast<float*>(out2), rows, seqlen, eps);
     else
         return DM_ERR_UNSUPPORTED;
@@ -405,6 +401,7 @@ p_sample_update_kernel(const float* __restrict__ model_out, const float* __restr
                        float* __restrict__ pred_xstart, int n, int chw, int T, int clip) {
     const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<int64_t>(n) * chw) return;
+    pdl_wait();
     const int b = static_cast<int>(idx / chw), r = static_cast<int>(idx % chw);
     const int64_t tt = t[b];
     // rows: 2 sqrt_recip_acp, 3 sqrt_recipm1_acp, 5 posterior_log_variance_clipped, 6 coef1, 7 coef2, 8 log_betas
@@ -431,8 +428,8 @@ extern "C" int dm_p_sample_update(const float* model_out, const float* x, const 
     if (!model_out || !x || !noise || !table || !t || !sample || batch <= 0 || chw <= 0 || n_steps <= 0)
         return DM_ERR_INVALID_ARG;
     const int64_t total = static_cast<int64_t>(batch) * chw;
-    dm::p_sample_update_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        model_out, x, noise, table, t, sample, pred_xstart, batch, chw, n_steps, clip_denoised);
+    dm::launch_pdl(dm::kPdlRow, dm::p_sample_update_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+                   static_cast<cudaStream_t>(stream), model_out, x, noise, table, t, sample, pred_xstart, batch, chw, n_steps, clip_denoised);
     DM_CUDA_TRY(cudaGetLastError());
     return DM_OK;
 }

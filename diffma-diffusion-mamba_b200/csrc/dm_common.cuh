@@ -15,6 +15,7 @@
 #error "diffma_b200 kernels are written for sm_100a (B200) only"
 #endif
 
+#include <utility>
 namespace dm {
 
 // ---- host-side status plumbing ----------------------------------------------------------------------
@@ -56,6 +57,39 @@ inline int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
 }
+
+// ---- programmatic dependent launch (PDL) ----
+// A kernel launched through launch_pdl() may start while its predecessor in the stream is still draining: its CTAs are
+// scheduled as SMs free up, run their prologue (index tables, weight staging -- nothing the predecessor writes) and block
+// in pdl_wait() until the predecessor grid has completed and its writes are visible.  Inside a captured CUDA graph the pair
+// becomes a programmatic edge.  pdl_wait() is a no-op in a kernel launched the ordinary way; DM_PDL=0 disables the attribute.
+#ifndef DM_PDL_DEFAULT
+#define DM_PDL_DEFAULT 7
+#endif
+enum : unsigned { kPdlRow = 1u, kPdlConvX = 2u, kPdlDelta = 4u, kPdlScan = 8u };
+inline unsigned pdl_mask() {                                   // DM_PDL = bit mask of the kernel classes above
+    static const int v = env_int("DM_PDL", DM_PDL_DEFAULT);
+    return static_cast<unsigned>(v);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(unsigned cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_mask() & cls) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -119,6 +119,7 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_acc = *tmem_slot;
+    pdl_launch_dependents();
 
     const int n_tiles = p.n_groups * tiles_per_group;
     int cur_group = -1;
@@ -176,6 +177,7 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
             if (load_w) cp_async16(w_dst + s * (kE * 128), w_src + s * kSl);
             cp_async_commit();
         };
+        if (tiles_done == 0u) pdl_wait();                                    // tables / barriers / TMEM are set up; xz is the predecessor's output
         stage(0);
         stage(1);
         // this thread's 8 rows: validity, A-operand offsets

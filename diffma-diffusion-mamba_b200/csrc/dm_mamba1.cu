@@ -553,6 +553,8 @@ __global__ void __launch_bounds__(128) m1_delta_kernel(const __grid_constant__ M
             v[i] = __ldg(reinterpret_cast<const uint4*>(G.x_dbl + static_cast<int64_t>(row) * kE) + (e & 7));
         }
     };
+    pdl_launch_dependents();
+    pdl_wait();                                  // W_dt is staged; x_dbl (kernel P's output) is read from here on
     uint4 av[4];
     fetch_a(0, av);
     float2 bias[8];
@@ -679,7 +681,9 @@ __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
                  __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
 }
 #ifndef DM_POLY_PAIRS
-#define DM_POLY_PAIRS 0       // of the 8 state pairs per (token, channel): how many decays are evaluated by exp2_poly2
+#define DM_POLY_PAIRS 1       // of the 8 state pairs per (token, channel): how many decays are evaluated by exp2_poly2
+                              // (r02, delta hand-over scan, B200: 0 -> 108.6 / 675 us at B16 L196 / B32 L784; 1 -> 106.5 / 652;
+                              //  2 -> 110.6 / 744; 3 -> 121 / 852: one pair is what the idle FMA issue slots absorb)
 #endif
 
 // non-volatile MMA: lets ptxas interleave independent accumulator chains
@@ -766,7 +770,10 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
         return v - 1;
     };
     int item = blockIdx.x;
-    if constexpr (kDyn) item = next_item();
+    if constexpr (kDyn) {
+        pdl_wait();                              // the ticket counters and every input belong to the predecessors
+        item = next_item();
+    }
   while (item < n_items) {
     int unit = item, seg = 0;
     if constexpr (kDyn) {
@@ -978,6 +985,7 @@ __global__ void __launch_bounds__(32, CPL == 2 ? 12 : DM_CPL1_MINB) m1_scan_kern
             }
     };
 
+    if constexpr (!kDyn) pdl_wait();             // constants are loaded; u / z / x_dbl / delta come from the predecessor kernels
     prefetch(c_begin);
     if constexpr (kDyn) {
         if (seg > 0) {                               // state left by the item that ran the previous segment of this unit
@@ -1154,7 +1162,7 @@ int launch_m1(const M1P& p_in, int phases, cudaStream_t stream, size_t sched_byt
                 const int rows = p.B * p.K * p.L;
                 const int tiles_per_group = (rows + p3::kTile - 1) / p3::kTile;
                 const int n_tiles = tiles_per_group * p.n_groups;
-                m1_conv_xproj_tc<<<n_tiles < n_sm ? n_tiles : n_sm, p3::kThreads, p3::kSmemBytes, stream>>>(p, rows, tiles_per_group);
+                DM_CUDA_TRY(launch_pdl(kPdlConvX, m1_conv_xproj_tc, dim3(n_tiles < n_sm ? n_tiles : n_sm), dim3(p3::kThreads), p3::kSmemBytes, stream, p, rows, tiles_per_group));
             }
         } else if (!split && p.D == 1024 && bytes2 <= 227 * 1024) {                 // persistent mma.sync kernel, W_x resident in shared memory
             static PerDeviceOnce cfg;
@@ -1180,7 +1188,7 @@ int launch_m1(const M1P& p_in, int phases, cudaStream_t stream, size_t sched_byt
             if (p.g[0].delta != nullptr) {                       // (all groups or none: normalised above)
                 const int rows = p.B * p.K * p.L;
                 const int grid = p.n_groups * ((rows + kDTok - 1) / kDTok) * (p.D / 256);
-                m1_delta_kernel<<<grid, 128, 0, stream>>>(p, rows);
+                DM_CUDA_TRY(launch_pdl(kPdlDelta, m1_delta_kernel, dim3(grid), dim3(128), 0, stream, p, rows));
                 DM_CUDA_TRY(cudaGetLastError());
             }
         }
@@ -1244,10 +1252,10 @@ int launch_m1(const M1P& p_in, int phases, cudaStream_t stream, size_t sched_byt
             for (int g = 0; g < p.n_groups; ++g)
                 if (p.g[g].chunk_states == nullptr) return DM_ERR_INVALID_ARG;      // all groups or none
             if (force_cpl == 2 || (force_cpl == 0 && units2 >= 8 * n_sm)) {
-                m1_scan_kernel<T, 2, false, true><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
+                DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 2, false, true>, dim3(units2), dim3(32), sizeof(ScanSmem<T, 2>), stream, p, units2));
             } else {
                 const int units1 = n_seq * (p.D / 32);
-                m1_scan_kernel<T, 1, false, true><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
+                DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 1, false, true>, dim3(units1), dim3(32), sizeof(ScanSmem<T, 1>), stream, p, units1));
             }
         } else if (force_cpl == 2 || (force_cpl == 0 && units2 >= 8 * n_sm)) {
             const int n_chunks = (p.L + kCH - 1) / kCH;
@@ -1273,37 +1281,37 @@ int launch_m1(const M1P& p_in, int phases, cudaStream_t stream, size_t sched_byt
                 bool done = false;
                 if constexpr (sizeof(T) == 2) {
                     if (delta_in) {
-                        m1_scan_kernel<T, 2, true, false, false, true><<<grid, 32, sizeof(ScanSmem<T, 2, true>), stream>>>(q, units2);
+                        DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 2, true, false, false, true>, dim3(grid), dim3(32), sizeof(ScanSmem<T, 2, true>), stream, q, units2));
                         done = true;
                     }
                 }
                 if (done) {
-                } else if (gated) m1_scan_kernel<T, 2, true, false, true><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
-                else m1_scan_kernel<T, 2, true, false><<<grid, 32, sizeof(ScanSmem<T, 2>), stream>>>(q, units2);
+                } else if (gated) DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 2, true, false, true>, dim3(grid), dim3(32), sizeof(ScanSmem<T, 2>), stream, q, units2));
+                else DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 2, true, false>, dim3(grid), dim3(32), sizeof(ScanSmem<T, 2>), stream, q, units2));
             } else {
                 bool done = false;
                 if constexpr (sizeof(T) == 2) {
                     if (delta_in) {
-                        m1_scan_kernel<T, 2, false, false, false, true><<<units2, 32, sizeof(ScanSmem<T, 2, true>), stream>>>(p, units2);
+                        DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 2, false, false, false, true>, dim3(units2), dim3(32), sizeof(ScanSmem<T, 2, true>), stream, p, units2));
                         done = true;
                     }
                 }
                 if (done) {
-                } else if (gated) m1_scan_kernel<T, 2, false, false, true><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
-                else m1_scan_kernel<T, 2, false, false><<<units2, 32, sizeof(ScanSmem<T, 2>), stream>>>(p, units2);
+                } else if (gated) DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 2, false, false, true>, dim3(units2), dim3(32), sizeof(ScanSmem<T, 2>), stream, p, units2));
+                else DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 2, false, false>, dim3(units2), dim3(32), sizeof(ScanSmem<T, 2>), stream, p, units2));
             }
         } else {
             const int units1 = n_seq * (p.D / 32);
             bool done = false;
             if constexpr (sizeof(T) == 2) {
                 if (delta_in) {
-                    m1_scan_kernel<T, 1, false, false, false, true><<<units1, 32, sizeof(ScanSmem<T, 1, true>), stream>>>(p, units1);
+                    DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 1, false, false, false, true>, dim3(units1), dim3(32), sizeof(ScanSmem<T, 1, true>), stream, p, units1));
                     done = true;
                 }
             }
             if (done) {
-            } else if (gated) m1_scan_kernel<T, 1, false, false, true><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
-            else m1_scan_kernel<T, 1, false, false><<<units1, 32, sizeof(ScanSmem<T, 1>), stream>>>(p, units1);
+            } else if (gated) DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 1, false, false, true>, dim3(units1), dim3(32), sizeof(ScanSmem<T, 1>), stream, p, units1));
+            else DM_CUDA_TRY(launch_pdl(kPdlScan, m1_scan_kernel<T, 1, false, false>, dim3(units1), dim3(32), sizeof(ScanSmem<T, 1>), stream, p, units1));
         }
         DM_CUDA_TRY(cudaGetLastError());
     }
