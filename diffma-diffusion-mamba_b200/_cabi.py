@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-DM_ABI_VERSION = 5
+DM_ABI_VERSION = 6
 DM_OK, DM_ERR_INVALID_ARG, DM_ERR_UNSUPPORTED, DM_ERR_CUDA = 0, -1, -2, -4
 DM_F32, DM_BF16 = 0, 1
 DM_MAX_GROUPS = 4
@@ -17,7 +17,7 @@ DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
 EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba1_bwd_chunk_tokens", "dm_mamba2_ssd_fwd", "dm_mamba2_ssd_bwd", "dm_merge_directions_multi", "dm_spiral_pre", "dm_spiral_post_ln",
            "dm_spiral_post_mix", "dm_spiral_post_mix_pre", "dm_spiral_pre_bwd", "dm_spiral_post_mix_bwd", "dm_spiral_post_ln_bwd",
-           "dm_merge_directions", "dm_gemm_bf16_tn", "dm_gemm_bf16_tn_ex", "dm_p_sample_update", "dm_adamw_ema_step", "dm_version", "dm_status_string", "dm_last_cuda_error",
+           "dm_merge_directions", "dm_gemm_bf16_tn", "dm_gemm_bf16_tn_ex", "dm_p_sample_update", "dm_adamw_ema_step", "dm_adamw_ema_step_ex", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
 
@@ -90,6 +90,16 @@ class Mamba2Args(C.Structure):
     ]
 
 
+class AdamwArgs(C.Structure):
+    """dm_adamw_args (include/diffma_b200.h)."""
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("ema", C.c_void_p), ("step", C.c_void_p), ("shadow_bf16", C.c_void_p), ("n", C.c_int64),
+        ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+        ("weight_decay", C.c_double), ("ema_decay", C.c_double), ("grad_scale", C.c_double),
+    ]
+
+
 _LIB = None
 
 
@@ -155,6 +165,8 @@ def lib() -> C.CDLL:
     L.dm_adamw_ema_step.restype = C.c_int
     f64 = C.c_double
     L.dm_adamw_ema_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, f64, f64, vp]
+    L.dm_adamw_ema_step_ex.restype = C.c_int
+    L.dm_adamw_ema_step_ex.argtypes = [C.POINTER(AdamwArgs), vp]
     if L.dm_version() != DM_ABI_VERSION:
         raise RuntimeError(f"diffma_b200: library ABI {L.dm_version()} != binding ABI {DM_ABI_VERSION}; rebuild")
     _LIB = L

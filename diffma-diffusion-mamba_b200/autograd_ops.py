@@ -531,6 +531,7 @@ class SpiralPostFn(torch.autograd.Function):
             x_out = ops.spiral_post_mix(x, sk, ab, hidden, w3f, b3f, mod)
         ctx.save_for_backward(ab, lnab, hidden, aw, l2w, w3f, b3f, mod)
         ctx.has_skip, ctx.BL, ctx.shapes = skip is not None, (B, L), (w3.shape, b3.shape)
+        ctx.att_dtypes = (att_w.dtype, att_b.dtype)           # fp32 masters, or bf16 leaves (ddp.FlatTrainState lowp)
         return x_out
 
     @staticmethod
@@ -540,5 +541,6 @@ class SpiralPostFn(torch.autograd.Function):
         with torch.autocast("cuda", enabled=False):
             d_ab, d_mod, d_l2w, d_l2b, d_aw, d_att_b, d_w3, d_b3 = ops.spiral_post_bwd(d_x_out, ab, lnab, hidden, aw, l2w, w3f,
                                                                                      b3f, mod, B, L)
+        d_aw, d_att_b = d_aw.to(ctx.att_dtypes[0]), d_att_b.to(ctx.att_dtypes[1])
         return (d_x_out, (d_x_out if ctx.has_skip else None), d_ab, d_l2w, d_l2b, d_aw, d_att_b, d_w3.view(ctx.shapes[0]),
                 d_b3.view(ctx.shapes[1]), d_mod)

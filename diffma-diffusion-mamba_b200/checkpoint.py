@@ -95,6 +95,11 @@ def save_checkpoint(path: str, net: torch.nn.Module, state=None, args=None) -> d
     """Write ``{"model", "ema", "opt", "args"}`` like train.py:293-300.  ``state``: the ``ddp.FlatTrainState`` that trains
     ``net`` (EMA + Adam moments); without one, ``ema`` is a copy of the model and ``opt`` is empty."""
     model_sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    if state is not None and hasattr(state, "master_state"):
+        # bf16 leaf weights (FlatTrainState lowp): the checkpoint holds the fp32 masters, as the reference's would
+        for k, v in state.master_state(net.named_parameters()).items():
+            if k in model_sd:
+                model_sd[k] = v.detach().cpu().clone()
     if state is not None and state.ema is not None:
         ema_named = state.ema_state(net.named_parameters())
         ema_sd = {k: (ema_named[k].detach().cpu().clone() if k in ema_named else v.clone()) for k, v in model_sd.items()}

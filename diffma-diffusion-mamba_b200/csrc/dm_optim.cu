@@ -16,6 +16,7 @@ namespace {
 
 struct AdamArgs {
     float* p; const float* g; float* m; float* v; float* ema;
+    __nv_bfloat16* shadow;       // optional: bf16 copy of the updated parameters (the compute-dtype weights of the next step)
     const float* step;           // device scalar: number of optimizer steps INCLUDING this one (t >= 1)
     int64_t n;
     // all derived on the host in double and rounded once (torch hands `1 - beta2` etc. to its kernels the same way)
@@ -55,6 +56,13 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(const AdamArgs a) {
         reinterpret_cast<float4*>(a.p)[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
         reinterpret_cast<float4*>(a.m)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
         reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        if (a.shadow != nullptr) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(pv[0], pv[1]), hi = __floats2bfloat162_rn(pv[2], pv[3]);
+            uint2 w;
+            w.x = *reinterpret_cast<const uint32_t*>(&lo);
+            w.y = *reinterpret_cast<const uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(a.shadow)[i] = w;
+        }
         if (a.ema != nullptr) {                                                  // ema.mul_(decay).add_(p, alpha = 1 - decay)
             e.x = fmaf(a.ema_decay, e.x, a.one_m_ema_decay * pv[0]);
             e.y = fmaf(a.ema_decay, e.y, a.one_m_ema_decay * pv[1]);
@@ -72,6 +80,7 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(const AdamArgs a) {
         const float v = fmaf(a.beta2, a.v[i], a.one_m_beta2 * g * g);
         p -= step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + a.eps));
         a.p[i] = p; a.m[i] = m; a.v[i] = v;
+        if (a.shadow != nullptr) a.shadow[i] = __float2bfloat16_rn(p);
         if (a.ema != nullptr) a.ema[i] = fmaf(a.ema_decay, a.ema[i], a.one_m_ema_decay * p);
     }
 }
@@ -79,31 +88,42 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(const AdamArgs a) {
 }  // namespace
 }  // namespace dm
 
-extern "C" int dm_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema,
-                                 const float* step, int64_t n, double lr, double beta1, double beta2, double eps,
-                                 double weight_decay, double ema_decay, double grad_scale, void* stream) {
+extern "C" int dm_adamw_ema_step_ex(const dm_adamw_args* x, void* stream) {
     using namespace dm;
-    if (!param || !grad || !exp_avg || !exp_avg_sq || !step || n <= 0) return DM_ERR_INVALID_ARG;
-    if (!aligned16(param) || !aligned16(grad) || !aligned16(exp_avg) || !aligned16(exp_avg_sq) || (ema && !aligned16(ema)))
+    if (!x || !x->param || !x->grad || !x->exp_avg || !x->exp_avg_sq || !x->step || x->n <= 0) return DM_ERR_INVALID_ARG;
+    if (!aligned16(x->param) || !aligned16(x->grad) || !aligned16(x->exp_avg) || !aligned16(x->exp_avg_sq) ||
+        (x->ema && !aligned16(x->ema)) || (x->shadow_bf16 && (reinterpret_cast<uintptr_t>(x->shadow_bf16) & 7u)))
         return DM_ERR_INVALID_ARG;
+    const double beta1 = x->beta1, beta2 = x->beta2, ema_decay = x->ema_decay;
     if (!(beta1 > 0. && beta1 < 1.) || !(beta2 > 0. && beta2 < 1.) || !(ema_decay >= 0. && ema_decay <= 1.))
         return DM_ERR_INVALID_ARG;
     int dev = 0, n_sm = 0;
     if (int e = current_device(&dev, &n_sm); e != DM_OK) return e;
     AdamArgs a{};
-    a.p = param; a.g = grad; a.m = exp_avg; a.v = exp_avg_sq; a.ema = ema; a.step = step; a.n = n;
+    a.p = x->param; a.g = x->grad; a.m = x->exp_avg; a.v = x->exp_avg_sq; a.ema = x->ema; a.step = x->step; a.n = x->n;
+    a.shadow = static_cast<__nv_bfloat16*>(x->shadow_bf16);
     a.beta1 = static_cast<float>(beta1); a.one_m_beta1 = static_cast<float>(1.0 - beta1);
     a.beta2 = static_cast<float>(beta2); a.one_m_beta2 = static_cast<float>(1.0 - beta2);
     a.log2_beta1 = static_cast<float>(log2(beta1)); a.log2_beta2 = static_cast<float>(log2(beta2));
-    a.lr = static_cast<float>(lr); a.eps = static_cast<float>(eps);
-    a.decay = static_cast<float>(1.0 - lr * weight_decay);
+    a.lr = static_cast<float>(x->lr); a.eps = static_cast<float>(x->eps);
+    a.decay = static_cast<float>(1.0 - x->lr * x->weight_decay);
     a.ema_decay = static_cast<float>(ema_decay); a.one_m_ema_decay = static_cast<float>(1.0 - ema_decay);
-    a.grad_scale = static_cast<float>(grad_scale);
+    a.grad_scale = static_cast<float>(x->grad_scale);
     // grid-stride, 8 CTAs of 256 threads per SM: enough 16-byte loads in flight to saturate HBM
-    const int64_t want = (n / 4 + 255) / 256;
+    const int64_t want = (x->n / 4 + 255) / 256;
     const int64_t cap = static_cast<int64_t>(n_sm) * 8;
     const int grid = static_cast<int>(want < 1 ? 1 : (want < cap ? want : cap));
     adamw_ema_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     DM_CUDA_TRY(cudaGetLastError());
     return DM_OK;
+}
+
+extern "C" int dm_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema,
+                                 const float* step, int64_t n, double lr, double beta1, double beta2, double eps,
+                                 double weight_decay, double ema_decay, double grad_scale, void* stream) {
+    dm_adamw_args x{};
+    x.param = param; x.grad = grad; x.exp_avg = exp_avg; x.exp_avg_sq = exp_avg_sq; x.ema = ema; x.step = step;
+    x.shadow_bf16 = nullptr; x.n = n; x.lr = lr; x.beta1 = beta1; x.beta2 = beta2; x.eps = eps;
+    x.weight_decay = weight_decay; x.ema_decay = ema_decay; x.grad_scale = grad_scale;
+    return dm_adamw_ema_step_ex(&x, stream);
 }

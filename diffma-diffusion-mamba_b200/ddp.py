@@ -23,6 +23,8 @@ from __future__ import annotations
 
 from typing import Iterable, List, Optional
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -32,7 +34,13 @@ _ALIGN = 64                      # elements (256 B): every parameter view stays 
 class FlatTrainState:
     def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int = 1, *, lr: float = 1e-4,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, ema_decay: Optional[float] = 0.9999,
-                 bucket_mib: float = 48.0, broadcast: bool = True, process_group=None, overlap: bool = True):
+                 bucket_mib: float = 48.0, broadcast: bool = True, process_group=None, overlap: bool = True,
+                 lowp: Optional[Iterable[torch.nn.Parameter]] = None):
+        """``lowp``: parameters that autocast consumes in bf16 only (``autocast_leaf_params(model)``).  Their fp32 masters
+        stay in the flat buffer, but the ``nn.Parameter`` the modules see becomes a bf16 LEAF aliasing a flat bf16 shadow
+        that the optimizer kernel refreshes: the forward needs no fp32 -> bf16 cast per weight, autograd hands back bf16
+        gradients with no bf16 -> fp32 cast per weight, and one multi-tensor copy per bucket moves them into the flat fp32
+        gradient buffer.  Same arithmetic as autocast over fp32 parameters (the forward sees bf16(master) either way)."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FlatTrainState: no trainable parameters")
@@ -51,14 +59,24 @@ class FlatTrainState:
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.step_t = torch.zeros((), dtype=torch.float32, device=dev)        # device-side step counter (graph replays)
+        lowp_ids = {id(p) for p in (lowp or ())}
+        self.is_lowp = [id(p) in lowp_ids for p in self.params]
+        self.flat_s = torch.zeros(off, dtype=torch.bfloat16, device=dev) if any(self.is_lowp) else None
+        self._g_views = [self.flat_g[o:o + p.numel()].view_as(p) for p, o in zip(self.params, offs)]
         with torch.no_grad():
-            for p, o in zip(self.params, offs):
+            for p, o, lp in zip(self.params, offs, self.is_lowp):
                 view = self.flat_p[o:o + p.numel()].view_as(p)
                 view.copy_(p.data)
-                p.data = view
-                p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+                if lp:
+                    p.data = self.flat_s[o:o + p.numel()].view_as(p)          # bf16 leaf; filled below
+                    p.grad = None
+                else:
+                    p.data = view
+                    p.grad = self.flat_g[o:o + p.numel()].view_as(p)
         if broadcast and world_size > 1:
             dist.broadcast(self.flat_p, src=0, group=process_group)           # what DDP's constructor does (train.py:153)
+        if self.flat_s is not None:
+            self.flat_s.copy_(self.flat_p)
         self.ema = self.flat_p.clone() if ema_decay is not None else None     # deepcopy(model) of train.py:156
         # ---- buckets: contiguous ranges of the flat gradient buffer, built from the END -----------------------
         want = int(bucket_mib * (1 << 20) / 4)
@@ -73,6 +91,9 @@ class FlatTrainState:
                 hi, n = offs[i], 0
         self._pending = [b[2] for b in self.buckets]
         self._fired = [False] * len(self.buckets)
+        self._flushed = [False] * len(self.buckets)
+        self._lowp_of_bucket = [[i for i in range(len(self.params)) if self.is_lowp[i] and self.bucket_of[i] == b]
+                                for b in range(len(self.buckets))]
         self.comm_stream = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and world_size > 1) else None
         self._hooks = []
         if world_size > 1 and overlap:
@@ -87,10 +108,20 @@ class FlatTrainState:
                 self._reduce_bucket(b)
         return hook
 
+    def _flush_lowp(self, b: int) -> None:
+        """bf16 leaf gradients of bucket ``b`` -> their fp32 slots in the flat gradient buffer (one multi-tensor copy)."""
+        if self._flushed[b]:
+            return
+        self._flushed[b] = True
+        idx = [i for i in self._lowp_of_bucket[b] if self.params[i].grad is not None]
+        if idx:
+            torch._foreach_copy_([self._g_views[i] for i in idx], [self.params[i].grad for i in idx])
+
     def _reduce_bucket(self, b: int) -> None:
         if self._fired[b]:
             return
         self._fired[b] = True
+        self._flush_lowp(b)
         lo, hi, _ = self.buckets[b]
         chunk = self.flat_g[lo:hi]
         if self.comm_stream is None:                                           # CPU (gloo) path of the tests
@@ -106,11 +137,18 @@ class FlatTrainState:
         self.flat_g.zero_()
         self._pending = [b[2] for b in self.buckets]
         self._fired = [False] * len(self.buckets)
+        self._flushed = [False] * len(self.buckets)
+        for p, lp in zip(self.params, self.is_lowp):
+            if lp:
+                p.grad = None                                                  # autograd then hands its bf16 result over as is
 
-    def finish_backward(self) -> None:
+    def finish_backward(self, reduce: bool = True) -> None:
         """After ``loss.backward()``: reduce whatever the hooks have not (unused parameters, overlap off) and make the
         compute stream wait for the communication stream.  Gradients hold the SUM over ranks afterwards."""
-        if self.world > 1:
+        if self.world == 1 or not self.overlap or not reduce:
+            for b in range(len(self.buckets)):
+                self._flush_lowp(b)
+        if self.world > 1 and reduce:
             if self.overlap:
                 for b in range(len(self.buckets)):
                     self._reduce_bucket(b)
@@ -121,7 +159,12 @@ class FlatTrainState:
 
     def check_views(self) -> None:
         gb, pb = self.flat_g.untyped_storage().data_ptr(), self.flat_p.untyped_storage().data_ptr()
-        for p in self.params:
+        sb = None if self.flat_s is None else self.flat_s.untyped_storage().data_ptr()
+        for p, lp in zip(self.params, self.is_lowp):
+            if lp:
+                if p.data.untyped_storage().data_ptr() != sb or p.dtype != torch.bfloat16:
+                    raise RuntimeError("FlatTrainState: a bf16 leaf parameter no longer aliases the flat shadow buffer")
+                continue
             if p.grad is None or p.grad.untyped_storage().data_ptr() != gb or p.data.untyped_storage().data_ptr() != pb:
                 raise RuntimeError("FlatTrainState: a parameter or its .grad no longer aliases the flat buffers "
                                    "(something called zero_grad(set_to_none=True), .to(), or replaced .data / .grad)")
@@ -134,12 +177,13 @@ class FlatTrainState:
         b1, b2 = self.betas
         if self.flat_p.is_cuda:
             from . import _cabi, ops
-            st = _cabi.lib().dm_adamw_ema_step(
+            args = _cabi.AdamwArgs(
                 self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                None if self.ema is None else self.ema.data_ptr(), self.step_t.data_ptr(), self.total, self.lr, b1, b2,
-                self.eps, self.weight_decay, 0.0 if self.ema_decay is None else self.ema_decay, scale,
-                torch.cuda.current_stream(self.flat_p.device).cuda_stream)
-            _cabi.check(st, "dm_adamw_ema_step")
+                None if self.ema is None else self.ema.data_ptr(), self.step_t.data_ptr(),
+                None if self.flat_s is None else self.flat_s.data_ptr(), self.total, self.lr, b1, b2, self.eps,
+                self.weight_decay, 0.0 if self.ema_decay is None else self.ema_decay, scale)
+            st = _cabi.lib().dm_adamw_ema_step_ex(C.byref(args), torch.cuda.current_stream(self.flat_p.device).cuda_stream)
+            _cabi.check(st, "dm_adamw_ema_step_ex")
             ops.LAUNCH_COUNTER["kernels"] += 1
             ops.invalidate_weight_caches()      # (a graph REPLAY of this call does not run this line: see replayed())
             return
@@ -153,12 +197,29 @@ class FlatTrainState:
         from . import ops
         ops.invalidate_weight_caches()
 
+    def master_state(self, named_params) -> dict:
+        """name -> fp32 master tensor (views into the flat parameter buffer).  With ``lowp`` leaves ``model.state_dict()``
+        holds their bf16 shadows; checkpoints (train.py:293-300 saves model.module.state_dict()) take the masters."""
+        by_id = {id(p): o for p, o in zip(self.params, self.offsets)}
+        return {n: self.flat_p[by_id[id(p)]:by_id[id(p)] + p.numel()].view_as(p) for n, p in named_params if id(p) in by_id}
+
     def ema_state(self, named_params) -> dict:
         """name -> EMA tensor (views into the flat EMA buffer), for checkpoints (train.py:293-300 saves ema.state_dict())."""
         if self.ema is None:
             raise RuntimeError("FlatTrainState was built without an EMA copy")
         by_id = {id(p): o for p, o in zip(self.params, self.offsets)}
         return {n: self.ema[by_id[id(p)]:by_id[id(p)] + p.numel()].view_as(p) for n, p in named_params if id(p) in by_id}
+
+
+_LOWP_SUFFIXES = ("in_proj.weight", "in_proj.bias", "out_proj.weight", "out_proj.bias", "adaLN_modulation.1.weight",
+                  "adaLN_modulation.1.bias", "attention_network.1.weight", "attention_network.1.bias")
+
+
+def autocast_leaf_params(model: torch.nn.Module) -> List[torch.nn.Parameter]:
+    """The big GEMM operands of every block (in/out projections, adaLN modulation, attention Linear): consumed only through
+    ``.to(bf16)`` / autocast ``F.linear`` -- candidates for ``FlatTrainState(lowp=...)``.  LayerNorm, conv1d, A_log, D,
+    dt_proj.bias and the small x_proj / dt_proj matrices stay fp32 leaves (the kernels read them in fp32 / split hi+lo)."""
+    return [p for n, p in model.named_parameters() if p.requires_grad and n.endswith(_LOWP_SUFFIXES)]
 
 
 class FlatGradSync:

@@ -691,7 +691,7 @@ def spiral_pre_bwd(x, skip, ln_weight, ln_bias, mod, w, d_out2, eps: float = 1e-
 def spiral_post_bwd(d_x_out, ab, lnab, hidden, att_w, ln2_weight, w3, b3, mod, B: int, L: int):
     """Adjoint of post_ln -> attention_network[1] -> post_mix.  d_x_out (B,L,D) fp32; ab (2, rows, D), lnab (rows, 2D),
     hidden (rows, D), att_w (D, 2D) in the act dtype.  Returns (d_ab (2, rows, D) act, d_mod (B, 3D) fp32 [gate part],
-    d_ln2_weight (2D), d_ln2_bias (2D), d_att_w (D, 2D) fp32, d_att_b (D) fp32, d_w3 (D), d_b3 (1))."""
+    d_ln2_weight (2D), d_ln2_bias (2D), d_att_w (D, 2D) act dtype, d_att_b (D) fp32, d_w3 (D), d_b3 (1))."""
     rows, D = hidden.shape
     dev = d_x_out.device
     d_ab = torch.empty_like(ab)
@@ -710,7 +710,7 @@ def spiral_post_bwd(d_x_out, ab, lnab, hidden, att_w, ln2_weight, w3, b3, mod, B
                                    d_w3.data_ptr(), d_b3.data_ptr(), B, L, D, code, st)
     _cabi.check(s, "dm_spiral_post_mix_bwd")
     d_lnab = torch.mm(d_hidden, att_w)                                        # (rows, 2D) act dtype
-    d_att_w = torch.mm(d_hidden.t(), lnab).float()                            # (D, 2D)
+    d_att_w = torch.mm(d_hidden.t(), lnab)                                    # (D, 2D) act dtype: the caller casts to the parameter's
     d_att_b = torch.sum(d_hidden, 0, dtype=torch.float32)
     s = lib.dm_spiral_post_ln_bwd(ab.data_ptr(), _f32c(ln2_weight, "ln2_weight").data_ptr(), d_lnab.data_ptr(),
                                   d_ab.data_ptr(), d_l2w.data_ptr(), d_l2b.data_ptr(), B, L, D, 1e-5, code, st)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 5
+#define DM_ABI_VERSION 6
 
 typedef enum {
     DM_OK = 0,
@@ -333,6 +333,18 @@ int dm_gemm_bf16_tn_ex(const dm_gemm_args* args, void* stream);
 int dm_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, const float* step,
                       int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay, double ema_decay,
                       double grad_scale, void* stream);   /* hyper-parameters in double: 1 - beta etc. are formed before rounding */
+/* Same update with the arguments in a struct and one more output: `shadow_bf16` (may be NULL, 8-byte aligned) receives
+ * the UPDATED parameters rounded to bf16 -- the compute-dtype weights of the next autocast step, so the training loop
+ * needs no per-tensor fp32 -> bf16 cast (reference: torch.autocast re-casts every weight in every forward, train.py:252). */
+typedef struct dm_adamw_args {
+    float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+    float* ema;                    /* may be NULL */
+    const float* step;             /* device scalar, as above */
+    void* shadow_bf16;             /* may be NULL */
+    int64_t n;
+    double lr, beta1, beta2, eps, weight_decay, ema_decay, grad_scale;
+} dm_adamw_args;
+int dm_adamw_ema_step_ex(const dm_adamw_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------ */
 int dm_version(void);                     /* DM_ABI_VERSION of the loaded library                        */

@@ -31,6 +31,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_cabi.Mamba1Args) == 10 * 4 + 8 + 4 * ctypes.sizeof(_cabi.Mamba1Group) + 16 + 8   # + sched workspace ptr/size (ABI 3), z_is_gated (ABI 5)
     assert ctypes.sizeof(_cabi.GemmArgs) == 13 * 8 + 6 * 4                                              # 104 + 24 = 128
     assert ctypes.sizeof(_cabi.Mamba2Group) == 15 * 8
+    assert ctypes.sizeof(_cabi.AdamwArgs) == 8 * 8 + 7 * 8                                               # ABI 6
     assert ctypes.sizeof(_cabi.Mamba2Args) == 11 * 4 + 4 + 8 + 4 * ctypes.sizeof(_cabi.Mamba2Group)
 
 

@@ -106,3 +106,37 @@ def test_diffma_checkpoint_roundtrip_in_reference_format(tmp_path):
         torch.testing.assert_close(back[i]["exp_avg"], e["exp_avg"])
         torch.testing.assert_close(back[i]["exp_avg_sq"], e["exp_avg_sq"])
     assert float(st2.step_t) == 3.0
+
+
+def test_bf16_leaf_state_saves_fp32_masters(tmp_path):
+    """FlatTrainState(lowp=autocast_leaf_params(net)): the modules hold bf16 leaves, the checkpoint still holds the fp32
+    masters (what the reference's model.module.state_dict() would contain), and the bf16 gradients autograd hands back
+    land in the flat fp32 gradient buffer."""
+    from diffma_b200 import checkpoint, model as M
+    from diffma_b200.ddp import FlatTrainState, autocast_leaf_params
+    torch.manual_seed(0)
+    net = M.DiffMa_models["DiffMa-S/7"](input_size=28, dt_rank=16, d_state=16, use_mamba2=False)
+    ref = {k: v.clone() for k, v in net.state_dict().items()}
+    lowp = autocast_leaf_params(net)
+    assert len(lowp) == 8 * len(net.blocks) + 2                         # + the final layer's adaLN Linear
+    st = FlatTrainState(net.parameters(), 1, ema_decay=0.5, lowp=lowp)
+    k = "blocks.1.mamba1.in_proj.weight"
+    p = dict(net.named_parameters())[k]
+    assert p.dtype == torch.bfloat16 and p.is_leaf and p.requires_grad and p.grad is None
+    torch.testing.assert_close(p.detach().float(), ref[k].to(torch.bfloat16).float(), rtol=0, atol=0)
+    assert dict(net.named_parameters())["blocks.1.norm1.weight"].dtype == torch.float32
+    st.check_views()
+    # a bf16 gradient arrives (as autograd would deliver it) and is moved into the flat fp32 buffer
+    st.begin_step()
+    (p.float().sum() * 2.0).backward()
+    assert p.grad is not None and p.grad.dtype == torch.bfloat16
+    st.finish_backward()
+    i = next(i for i, q in enumerate(st.params) if q is p)
+    torch.testing.assert_close(st.flat_g[st.offsets[i]:st.offsets[i] + p.numel()], torch.full((p.numel(),), 2.0))
+    path = str(tmp_path / "0000001.pt")
+    ck = checkpoint.save_checkpoint(path, net, st, argparse.Namespace(model="DiffMa-S/7"))
+    assert ck["model"][k].dtype == torch.float32
+    torch.testing.assert_close(ck["model"][k], ref[k], rtol=0, atol=0)
+    fresh = M.DiffMa_models["DiffMa-S/7"](input_size=28, dt_rank=16, d_state=16, use_mamba2=False)
+    checkpoint.load_checkpoint(path, fresh, kind="model")
+    torch.testing.assert_close(fresh.state_dict()[k], ref[k], rtol=0, atol=0)

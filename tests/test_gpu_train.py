@@ -97,3 +97,56 @@ def test_flat_train_state_matches_torch_adamw_and_ema(dev):
         torch.testing.assert_close(p, pr, rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(ema[name], pe, rtol=1e-5, atol=1e-6)
     state.check_views()
+
+
+def test_bf16_leaf_weights_train_like_autocast_over_fp32_masters(dev):
+    """FlatTrainState(lowp=...): the block GEMM weights become bf16 leaves over fp32 masters (no per-weight casts in the
+    step).  Same arithmetic as autocast over fp32 parameters: after 3 steps on DiffMa-S/4 the fp32 masters, the EMA and the
+    losses agree with the all-fp32-leaf run to rounding (the only difference: gradients of shared-dtype sums)."""
+    from diffma_b200 import create_model_and_diffusion, synth
+    from diffma_b200.ddp import FlatTrainState, autocast_leaf_params
+    results = []
+    for use_lowp in (False, True):
+        torch.manual_seed(0)
+        net, diffusion = create_model_and_diffusion("DiffMa-S/4", respacing="")
+        synth.fill_trained_like_(net, seed=11)
+        net = net.to(dev).train()
+        lowp = autocast_leaf_params(net) if use_lowp else None
+        if use_lowp:
+            assert len(lowp) >= 8 * len(net.blocks)
+        state = FlatTrainState(net.parameters(), 1, lr=1e-3, ema_decay=0.9, lowp=lowp)
+        b = synth.synthetic_batch(4, tokens=49, seed=100, device=dev)
+        kw = dict(y=b["y"], y2=b["y2"], w=b["w"])
+        g = torch.Generator(device=dev).manual_seed(5)
+        losses = []
+        for _ in range(3):
+            t = torch.randint(0, diffusion.num_timesteps, (4,), device=dev, generator=g)
+            noise = torch.randn(b["x"].shape, device=dev, generator=g)
+            with torch.enable_grad():
+                state.begin_step()
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss = diffusion.training_losses(net, b["x"], t, kw, noise=noise)["loss"].mean()
+                loss.backward()
+                state.finish_backward()
+                state.optimizer_step()
+            losses.append(float(loss.detach()))
+        state.check_views()
+        if use_lowp:
+            for p, lp in zip(state.params, state.is_lowp):
+                assert (p.dtype == torch.bfloat16) == lp
+            # the shadow the modules see is bf16(master) after every step
+            torch.testing.assert_close(state.flat_s.float(), state.flat_p.to(torch.bfloat16).float(), rtol=0, atol=0)
+        results.append((losses, state.flat_p.clone(), state.ema.clone(), state.flat_g.clone()))
+    (l0, p0, e0, g0), (l1, p1, e1, g1) = results
+    assert l0[0] == pytest.approx(l1[0], rel=1e-6)                 # first forward: identical weights
+    for a, c in zip(l0, l1):
+        assert a == pytest.approx(c, rel=2e-2)
+    # gradients of the last step: same values up to bf16 rounding of single terms
+    denom = g0.abs().max().clamp_min(1e-12)
+    assert float((g0 - g1).abs().max() / denom) < 5e-2
+    # Adam normalises the update: compare the moved distance, not the raw values
+    # (a near-zero gradient whose sign differs between the runs moves a weight by up to 2 lr per step; the backward's
+    #  atomics already make two runs of the SAME configuration differ that way)
+    torch.testing.assert_close(p1, p0, rtol=0, atol=2 * 3 * 1e-3 * 1.1)
+    assert float((p1 - p0).abs().mean()) < 2e-4
+    torch.testing.assert_close(e1, e0, rtol=0, atol=1e-3)

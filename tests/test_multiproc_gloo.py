@@ -212,6 +212,58 @@ def test_flat_train_state_bucketed_sync_equals_single_process_gradient():
             torch.testing.assert_close(torch.from_numpy(a), p.grad, rtol=1e-5, atol=1e-6)
 
 
+def _lowp_state_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from diffma_b200.ddp import FlatTrainState
+    torch.manual_seed(rank)
+    net = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.SiLU(), torch.nn.Linear(16, 3))
+    lowp = [net[0].weight, net[2].weight]
+    state = FlatTrainState(net.parameters(), world, bucket_mib=0.0002, lowp=lowp)
+    assert net[0].weight.dtype == torch.bfloat16 and net[0].bias.dtype == torch.float32
+    x = torch.randn(4, 12, generator=torch.Generator().manual_seed(7 + rank))
+    ok = True
+    with torch.enable_grad():
+        for _ in range(2):
+            state.begin_step()
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                net(x).float().square().mean().backward()
+            local = [p.grad.detach().float().clone() for p in lowp]          # bf16 results of this rank's backward
+            state.finish_backward()
+            state.check_views()
+            for p, mine in zip(lowp, local):
+                parts = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(parts, mine)
+                i = next(i for i, q_ in enumerate(state.params) if q_ is p)
+                ok = ok and torch.allclose(state._g_views[i], sum(parts), rtol=1e-6, atol=1e-7)
+    # every rank holds rank 0's weights: fp32 masters and their bf16 shadows
+    w0 = [state.flat_p.clone(), state.flat_s.float().clone()]
+    for t in w0:
+        dist.broadcast(t, src=0)
+    ok = ok and torch.equal(w0[0], state.flat_p) and torch.equal(w0[1], state.flat_s.float())
+    if rank == 0:
+        q.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_flat_train_state_bf16_leaves_sum_over_ranks():
+    """FlatTrainState(lowp=...) on 2 gloo ranks: the bf16 gradients autograd hands to the leaf weights are copied into the
+    flat fp32 buffer bucket by bucket before that bucket's all-reduce; the result is the SUM over ranks, and masters +
+    shadows were broadcast from rank 0."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29350 + os.getpid() % 200
+    procs = [ctx.Process(target=_lowp_state_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
+
+
 def test_reference_arm_under_torchrun_prints_once():
     env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",

@@ -28,7 +28,7 @@ def run(model="DiffMa-XL/4", batch=32, steps=10, warmup=3, world=1, rank=0, devi
     """Build the model + flat training state, capture the step, time ``steps`` steps.  Returns the result dict (every
     rank; only rank 0's is printed by callers).  The process group must already exist when world > 1."""
     from diffma_b200 import _cabi, create_model_and_diffusion, ops, synth
-    from diffma_b200.ddp import FlatTrainState
+    from diffma_b200.ddp import FlatTrainState, autocast_leaf_params
     _cabi.lib()
     if global_batch:
         if global_batch % world:
@@ -39,8 +39,10 @@ def run(model="DiffMa-XL/4", batch=32, steps=10, warmup=3, world=1, rank=0, devi
     net, diffusion = create_model_and_diffusion(model, use_mamba2=mamba2, respacing="")
     synth.fill_trained_like_(net, seed=11)
     net = net.to(device).train()
+    # bf16 leaves for the block GEMM weights (fp32 masters in the flat state): no per-weight casts in the step
+    lowp = autocast_leaf_params(net) if (not fp32 and os.environ.get("DIFFMA_LOWP", "1") != "0") else None
     state = FlatTrainState(net.parameters(), world, lr=1e-4, weight_decay=0.0, ema_decay=0.9999 if ema else None,
-                           overlap=overlap)
+                           overlap=overlap, lowp=lowp)
     patch = int(model.split("/")[1])
     L = (28 // patch) ** 2
     b = synth.synthetic_batch(batch, tokens=L, seed=100 + rank, device=device)
@@ -57,8 +59,7 @@ def run(model="DiffMa-XL/4", batch=32, steps=10, warmup=3, world=1, rank=0, devi
         if not sync:                                     # comparison graph: same step without the collective
             state._fired = [True] * len(state.buckets)   # (the hooks then find every bucket already handled)
         loss.backward()                                  # bucket all-reduces fork onto the comm stream from the hooks
-        if sync:
-            state.finish_backward()                      # join: gradients hold the SUM over ranks
+        state.finish_backward(reduce=sync)               # join: gradients hold the SUM over ranks
         loss_buf.copy_(loss.detach())
         state.optimizer_step()                           # AdamW + EMA, 1/world folded in: one kernel
 
