@@ -121,8 +121,16 @@ class Mamba1ScanFn(torch.autograd.Function):
         E = x_dbl.shape[-1]
         N = weights[0].A.shape[1]
         R = E - 2 * N
-        dout = dout.to(x0.dtype).contiguous()
-        a, _ = ops.mamba1_args(xz, weights, plan, bufs=(dout, u, x_dbl))
+        dout = dout.to(x0.dtype)
+        ostr = None
+        if (plan.layout == "concat" and dout.dim() == 5 and dout.stride(4) == 1 and not dout.is_contiguous()
+                and all(st % 8 == 0 for st in dout.stride()[:4]) and dout.data_ptr() % 16 == 0
+                and (G == 1 or dout.stride(0) > 0)):
+            # e.g. the gradient of a sum over the directions: an expanded view (direction stride 0) the kernel reads as is
+            ostr = (dout.stride(1), dout.stride(3), dout.stride(2))                          # (batch, direction, token)
+        else:
+            dout = dout.contiguous()
+        a, _ = ops.mamba1_args(xz, weights, plan, bufs=(dout, u, x_dbl), out_strides=ostr)
         f32 = dict(dtype=torch.float32, device=dev)
         W = weights[0].conv_weight.shape[1]
         d_xz_scan = torch.empty((G, B, K, L, 2 * D), **f32)

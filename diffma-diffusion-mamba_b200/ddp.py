@@ -8,8 +8,11 @@ rest of the backward; then ``opt.step()`` (AdamW, lr 1e-4, weight decay 0: train
 ``FlatTrainState`` keeps the same semantics -- broadcast at construction, gradients AVERAGED over ranks, AdamW, EMA --
 but lays the state out so that the whole step is ONE CUDA graph per rank:
 
-* parameters, gradients, both Adam moments and the EMA copy are five flat fp32 buffers; every ``p.data`` / ``p.grad``
-  is a view into them (autograd accumulates into an existing ``.grad`` in place), offsets 256-byte aligned;
+* parameters, gradients, both Adam moments and the EMA copy are five flat fp32 buffers, offsets 256-byte aligned.
+  ``p.data`` is a view into the parameter buffer (or, for the ``lowp`` GEMM weights, a bf16 leaf aliasing a flat bf16
+  shadow the optimizer kernel refreshes).  ``.grad`` is cleared at ``begin_step`` so autograd hands its result tensors
+  over as they are; one multi-tensor copy per bucket moves them into the flat gradient buffer (no accumulate / cast
+  kernel per parameter), and after ``finish_backward`` every fp32 ``.grad`` is the view of its reduced slot again;
 * the gradient buffer is cut into buckets from its END (the backward produces the last blocks' gradients first).  A
   post-accumulate hook per parameter counts a bucket down; when it is complete its all-reduce (NCCL over NVLink /
   NVSwitch, SUM) is enqueued on a communication stream while the backward of the earlier blocks keeps running on the
@@ -92,8 +95,7 @@ class FlatTrainState:
         self._pending = [b[2] for b in self.buckets]
         self._fired = [False] * len(self.buckets)
         self._flushed = [False] * len(self.buckets)
-        self._lowp_of_bucket = [[i for i in range(len(self.params)) if self.is_lowp[i] and self.bucket_of[i] == b]
-                                for b in range(len(self.buckets))]
+        self._of_bucket = [[i for i in range(len(self.params)) if self.bucket_of[i] == b] for b in range(len(self.buckets))]
         self.comm_stream = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and world_size > 1) else None
         self._hooks = []
         if world_size > 1 and overlap:
@@ -108,12 +110,13 @@ class FlatTrainState:
                 self._reduce_bucket(b)
         return hook
 
-    def _flush_lowp(self, b: int) -> None:
-        """bf16 leaf gradients of bucket ``b`` -> their fp32 slots in the flat gradient buffer (one multi-tensor copy)."""
+    def _flush(self, b: int) -> None:
+        """The gradients autograd produced for bucket ``b`` (fp32, or bf16 for the lowp leaves) -> their fp32 slots in the
+        flat gradient buffer: one multi-tensor copy instead of one accumulate kernel per parameter."""
         if self._flushed[b]:
             return
         self._flushed[b] = True
-        idx = [i for i in self._lowp_of_bucket[b] if self.params[i].grad is not None]
+        idx = [i for i in self._of_bucket[b] if self.params[i].grad is not None]
         if idx:
             torch._foreach_copy_([self._g_views[i] for i in idx], [self.params[i].grad for i in idx])
 
@@ -121,7 +124,7 @@ class FlatTrainState:
         if self._fired[b]:
             return
         self._fired[b] = True
-        self._flush_lowp(b)
+        self._flush(b)
         lo, hi, _ = self.buckets[b]
         chunk = self.flat_g[lo:hi]
         if self.comm_stream is None:                                           # CPU (gloo) path of the tests
@@ -132,22 +135,22 @@ class FlatTrainState:
             dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
 
     def begin_step(self) -> None:
-        """Zero every gradient with one kernel and re-arm the buckets (do NOT call ``zero_grad(set_to_none=True)``: it
-        would detach the views)."""
+        """Zero the flat gradient buffer with one kernel, re-arm the buckets and clear every ``.grad``: autograd then hands
+        its result tensors over as they are (no accumulate kernel per parameter); ``_flush`` copies them into the flat
+        buffer bucket by bucket and ``finish_backward`` points every ``.grad`` at its (reduced) slot again."""
         self.flat_g.zero_()
         self._pending = [b[2] for b in self.buckets]
         self._fired = [False] * len(self.buckets)
         self._flushed = [False] * len(self.buckets)
-        for p, lp in zip(self.params, self.is_lowp):
-            if lp:
-                p.grad = None                                                  # autograd then hands its bf16 result over as is
+        for p in self.params:
+            p.grad = None
 
     def finish_backward(self, reduce: bool = True) -> None:
         """After ``loss.backward()``: reduce whatever the hooks have not (unused parameters, overlap off) and make the
         compute stream wait for the communication stream.  Gradients hold the SUM over ranks afterwards."""
         if self.world == 1 or not self.overlap or not reduce:
             for b in range(len(self.buckets)):
-                self._flush_lowp(b)
+                self._flush(b)
         if self.world > 1 and reduce:
             if self.overlap:
                 for b in range(len(self.buckets)):
@@ -156,6 +159,9 @@ class FlatTrainState:
                 dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)   # one blocking collective
             if self.comm_stream is not None:
                 torch.cuda.current_stream().wait_stream(self.comm_stream)
+        for p, lp, v in zip(self.params, self.is_lowp, self._g_views):
+            if not lp:
+                p.grad = v               # fp32 leaves: ``.grad`` is the (summed) slot of the flat buffer again
 
     def check_views(self) -> None:
         gb, pb = self.flat_g.untyped_storage().data_ptr(), self.flat_p.untyped_storage().data_ptr()
@@ -165,7 +171,7 @@ class FlatTrainState:
                 if p.data.untyped_storage().data_ptr() != sb or p.dtype != torch.bfloat16:
                     raise RuntimeError("FlatTrainState: a bf16 leaf parameter no longer aliases the flat shadow buffer")
                 continue
-            if p.grad is None or p.grad.untyped_storage().data_ptr() != gb or p.data.untyped_storage().data_ptr() != pb:
+            if (p.grad is not None and p.grad.untyped_storage().data_ptr() != gb) or p.data.untyped_storage().data_ptr() != pb:
                 raise RuntimeError("FlatTrainState: a parameter or its .grad no longer aliases the flat buffers "
                                    "(something called zero_grad(set_to_none=True), .to(), or replaced .data / .grad)")
 
@@ -212,13 +218,14 @@ class FlatTrainState:
 
 
 _LOWP_SUFFIXES = ("in_proj.weight", "in_proj.bias", "out_proj.weight", "out_proj.bias", "adaLN_modulation.1.weight",
-                  "adaLN_modulation.1.bias", "attention_network.1.weight", "attention_network.1.bias")
+                  "adaLN_modulation.1.bias", "attention_network.1.weight", "attention_network.1.bias", "x_proj.weight",
+                  "dt_proj.weight")
 
 
 def autocast_leaf_params(model: torch.nn.Module) -> List[torch.nn.Parameter]:
     """The big GEMM operands of every block (in/out projections, adaLN modulation, attention Linear): consumed only through
-    ``.to(bf16)`` / autocast ``F.linear`` -- candidates for ``FlatTrainState(lowp=...)``.  LayerNorm, conv1d, A_log, D,
-    dt_proj.bias and the small x_proj / dt_proj matrices stay fp32 leaves (the kernels read them in fp32 / split hi+lo)."""
+    ``.to(bf16)`` / autocast ``F.linear`` -- candidates for ``FlatTrainState(lowp=...)``.  LayerNorm, conv1d, A_log, D and
+    dt_proj.bias stay fp32 leaves (the kernels read them in fp32)."""
     return [p for n, p in model.named_parameters() if p.requires_grad and n.endswith(_LOWP_SUFFIXES)]
 
 

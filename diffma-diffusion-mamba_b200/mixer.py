@@ -17,6 +17,8 @@ from __future__ import annotations
 import math
 from typing import List, Optional, Sequence
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -210,6 +212,9 @@ class Mamba2(_MixerBase):
 # ------------------------------------------------------------------------------------------------------
 # the fused forward of one or several mixers of the same kind
 # ------------------------------------------------------------------------------------------------------
+_SUM_FIRST = os.environ.get("DIFFMA_SUM_FIRST", "1") != "0"     # training out-projection: sum the directions before the GEMM
+
+
 def _act_dtype(x: torch.Tensor):
     if torch.is_autocast_enabled():
         dt = torch.get_autocast_dtype("cuda")
@@ -254,9 +259,20 @@ def mix_groups(mixers: Sequence[nn.Module], inputs: Sequence[torch.Tensor], scan
         outs = []
         if not is_m2:
             y = ops.mamba1_scan(proj, [m.scan_weights(act) for m in mixers], plan)
+            if _SUM_FIRST and torch.is_grad_enabled() and plan.layout == "concat" and plan.n_dir > 1 and y.requires_grad:
+                # training: sum the directions first (one kernel for all groups; its adjoint is an expanded view the
+                # reverse-scan kernel reads with direction stride 0), then a K = d_inner projection per group -- instead of
+                # a repeated (d_model, K * d_inner) weight per step, its summed gradient, and per-group slices of y whose
+                # adjoints each zero-fill and add a full (G, B, L, K, D) tensor
+                ys = y.sum(3).unbind(0)
+                for g, m in enumerate(mixers):
+                    bias = None if m.out_proj.bias is None else m.out_proj.bias.to(act) * plan.n_dir
+                    outs.append(F.linear(ys[g], m.out_proj.weight.to(act), bias))
+                return outs
+            yg = y.unbind(0)
             for g, m in enumerate(mixers):
                 bias = None if m.out_proj.bias is None else m.out_proj.bias.to(act)
-                outs.append(_merge_out_proj(y[g], plan, m.out_proj.weight.to(act), bias, scan_type, False))
+                outs.append(_merge_out_proj(yg[g], plan, m.out_proj.weight.to(act), bias, scan_type, False))
             return outs
         v, ss = ops.mamba2_ssd(proj, [m.scan_weights() for m in mixers], plan, m0.d_inner, m0.d_state, m0.nheads,
                                gate=True, want_sumsq=True)

@@ -226,7 +226,7 @@ def _sched_workspace(device, batch: int, n_dir: int, d_inner: int, groups: int):
 
 
 def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: ScanPlan, bufs=None, dynamic=None,
-                chunk_states=None, z_gated: bool = False, delta=None):
+                chunk_states=None, z_gated: bool = False, delta=None, out_strides=None):
     """Fill a ``dm_mamba1_args`` for the given groups.  Returns (args, (out, u, x_dbl)); the tensors own the memory
     the struct points at and must outlive the launch.  ``bufs`` = existing (out-shaped, u, x_dbl) tensors to point at
     instead of allocating (the backward passes dout / the saved intermediates)."""
@@ -250,7 +250,9 @@ def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: Scan
         ws = _sched_workspace(x0.device, B, plan.n_dir, D, G)
         if ws is not None:
             a.sched_workspace, a.sched_workspace_bytes = ws.data_ptr(), ws.numel()
-    obs, ods, ots = plan.out_strides(D)
+    # (batch, direction, token) strides of the out-shaped buffer; ``out_strides`` overrides them for a strided view (the
+    # backward reads an upstream gradient that may be broadcast over the directions: direction stride 0)
+    obs, ods, ots = plan.out_strides(D) if out_strides is None else out_strides
     # one allocation per kind so groups are adjacent (lets callers view them as a batch)
     if bufs is None:
         out_all = torch.empty((G,) + plan.out_shape(B, D), dtype=x0.dtype, device=x0.device)
@@ -258,7 +260,7 @@ def mamba1_args(xz: List[torch.Tensor], weights: List[Mamba1Weights], plan: Scan
         xd_all = torch.empty((G, B, plan.n_dir, plan.seqlen, E), dtype=torch.float32, device=x0.device)
     else:
         out_all, u_all, xd_all = bufs
-        assert out_all.is_contiguous() and u_all.is_contiguous() and xd_all.is_contiguous()
+        assert (out_strides is not None or out_all.is_contiguous()) and u_all.is_contiguous() and xd_all.is_contiguous()
         assert tuple(out_all.shape) == (G,) + plan.out_shape(B, D) and out_all.dtype == x0.dtype
     for g in range(G):
         x, w = xz[g], weights[g]

@@ -118,7 +118,7 @@ def test_bf16_leaf_state_saves_fp32_masters(tmp_path):
     net = M.DiffMa_models["DiffMa-S/7"](input_size=28, dt_rank=16, d_state=16, use_mamba2=False)
     ref = {k: v.clone() for k, v in net.state_dict().items()}
     lowp = autocast_leaf_params(net)
-    assert len(lowp) == 8 * len(net.blocks) + 2                         # + the final layer's adaLN Linear
+    assert len(lowp) == 12 * len(net.blocks) + 2       # per block 2 x (in, out, x_proj, dt_proj) + adaLN W, b + attention W, b; + final adaLN
     st = FlatTrainState(net.parameters(), 1, ema_decay=0.5, lowp=lowp)
     k = "blocks.1.mamba1.in_proj.weight"
     p = dict(net.named_parameters())[k]

@@ -113,7 +113,7 @@ def test_bf16_leaf_weights_train_like_autocast_over_fp32_masters(dev):
         net = net.to(dev).train()
         lowp = autocast_leaf_params(net) if use_lowp else None
         if use_lowp:
-            assert len(lowp) >= 8 * len(net.blocks)
+            assert len(lowp) >= 12 * len(net.blocks)
         state = FlatTrainState(net.parameters(), 1, lr=1e-3, ema_decay=0.9, lowp=lowp)
         b = synth.synthetic_batch(4, tokens=49, seed=100, device=dev)
         kw = dict(y=b["y"], y2=b["y2"], w=b["w"])

@@ -21,12 +21,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="DiffMa-XL/4")
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--mamba2", action="store_true")
+ap.add_argument("--no-lowp", action="store_true", help="fp32 leaf weights (autocast casts every weight every step)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 net, diffusion = create_model_and_diffusion(a.model, use_mamba2=a.mamba2, respacing="")
 synth.fill_trained_like_(net, seed=11)
 net = net.to(dev).train()
-opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0, fused=True)
+from diffma_b200.ddp import FlatTrainState, autocast_leaf_params  # noqa: E402
+state = FlatTrainState(net.parameters(), 1, lr=1e-4, weight_decay=0.0, ema_decay=0.9999,
+                       lowp=None if a.no_lowp else autocast_leaf_params(net))
 patch = int(a.model.split("/")[1])
 L = (28 // patch) ** 2
 b = synth.synthetic_batch(a.batch, tokens=L, seed=100, device=dev)
@@ -34,12 +37,13 @@ kw = dict(y=b["y"], y2=b["y2"], w=b["w"])
 
 
 def step():
+    state.begin_step()
     t = torch.randint(0, diffusion.num_timesteps, (a.batch,), device=dev)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         loss = diffusion.training_losses(net, b["x"], t, kw)["loss"].mean()
-    opt.zero_grad(set_to_none=True)
     loss.backward()
-    opt.step()
+    state.finish_backward()
+    state.optimizer_step()
 
 
 for _ in range(3):
@@ -50,7 +54,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     torch.cuda.synchronize()
 # device time by the ATen / autograd op that launched the kernels (which part of the eager glue costs what)
 ops_rows = []
-for e in sorted(prof.key_averages(), key=lambda e: -getattr(e, "self_device_time_total", 0))[:40]:
+for e in sorted(prof.key_averages(), key=lambda e: -getattr(e, "self_device_time_total", 0))[:60]:
     t = getattr(e, "self_device_time_total", 0)
     if t > 0:
         ops_rows.append({"op": e.key[:60], "calls": e.count, "self_device_us": round(t, 1)})

@@ -24,7 +24,7 @@ import torch  # noqa: E402
 
 
 def run(model="DiffMa-XL/4", batch=32, steps=10, warmup=3, world=1, rank=0, device=None, mamba2=False, fp32=False,
-        use_graph=True, overlap=True, global_batch=0, measure_exposed=True, ema=True):
+        use_graph=True, overlap=True, global_batch=0, measure_exposed=True, ema=True, repeats=5):
     """Build the model + flat training state, capture the step, time ``steps`` steps.  Returns the result dict (every
     rank; only rank 0's is printed by callers).  The process group must already exist when world > 1."""
     from diffma_b200 import _cabi, create_model_and_diffusion, ops, synth
@@ -126,14 +126,22 @@ def run(model="DiffMa-XL/4", batch=32, steps=10, warmup=3, world=1, rank=0, devi
         return float(t.item())
 
     n0 = ops.LAUNCH_COUNTER["kernels"]
-    sec = timed("sync", steps)
+    # every repetition times exactly `steps` steps; the median repetition is reported (single short runs on a B200 that is
+    # still settling its clocks under the step's power draw differ by up to 5 %)
+    from bench import ClockSampler                       # nvidia-smi clocks / throttle reasons during the timed region
+    secs, clocks = [], []
+    for _ in range(max(1, repeats)):
+        with ClockSampler(device.index if device.index is not None else 0) as cs:
+            secs.append(timed("sync", steps))
+        clocks.append(cs.summary())
+    sec = sorted(secs)[len(secs) // 2]
     loss = float(loss_buf.item())
-    own_launches = (ops.LAUNCH_COUNTER["kernels"] - n0)
+    own_launches = (ops.LAUNCH_COUNTER["kernels"] - n0) // max(1, repeats)
     exposed = None
     if world > 1 and measure_exposed and "nosync" in graphs:
         # NOTE: without the collective the ranks' weights drift apart; this variant is timed AFTER the real one and only
         # to quantify how much of the all-reduce is not hidden behind the backward
-        sec_ns = timed("nosync", steps)
+        sec_ns = sorted(timed("nosync", steps) for _ in range(max(1, repeats)))[max(1, repeats) // 2]
         exposed = round((sec - sec_ns) / steps * 1e3, 3)
     nparam = sum(p.numel() for p in net.parameters() if p.requires_grad)
     return {
@@ -145,6 +153,10 @@ def run(model="DiffMa-XL/4", batch=32, steps=10, warmup=3, world=1, rank=0, devi
                                f"{'DDP all-reduce + ' if world > 1 else ''}AdamW + EMA), L={L}, per-GPU batch {batch}",
                    "global_batch": world * batch, "grad_allreduce_mib": round(nparam * 4 / 2 ** 20, 1),
                    "buckets": len(state.buckets)},
+        "clocks": {"sm_mhz_each": [c["sm_mhz"] for c in clocks], "sm_max_mhz": clocks[0]["sm_max_mhz"],
+                   "reasons": sorted({r for c in clocks for r in c["reasons"]})},
+        "timing": {"repeats": len(secs), "ms_per_step_each": [round(x / steps * 1e3, 3) for x in secs],
+                   "note": "each repetition times exactly `steps` steps (CUDA events, max over ranks); median reported"},
         "loss": round(loss, 5), "cuda_graph": "sync" in graphs, "capture_note": capture_note,
         "exposed_allreduce_ms": exposed,
         "grad_sync": "none" if world == 1 else (
@@ -169,6 +181,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="one blocking all-reduce after the backward")
     ap.add_argument("--no-ema", action="store_true")
+    ap.add_argument("--repeats", type=int, default=5, help="timed repetitions of `steps` steps each; the median is reported")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -180,7 +193,7 @@ def main():
         torch.distributed.init_process_group("nccl", rank=rank, world_size=world)
     res = run(model=args.model, batch=args.batch, steps=args.steps, warmup=args.warmup, world=world, rank=rank,
               device=device, mamba2=args.mamba2, fp32=args.fp32, use_graph=not args.no_graph,
-              overlap=not args.no_overlap, global_batch=args.global_batch, ema=not args.no_ema)
+              overlap=not args.no_overlap, global_batch=args.global_batch, ema=not args.no_ema, repeats=args.repeats)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
