@@ -128,7 +128,8 @@ def test_bf16_leaf_state_saves_fp32_masters(tmp_path):
     st.check_views()
     # a bf16 gradient arrives (as autograd would deliver it) and is moved into the flat fp32 buffer
     st.begin_step()
-    (p.float().sum() * 2.0).backward()
+    with torch.enable_grad():                               # other test modules switch grad mode off process-wide
+        (p.float().sum() * 2.0).backward()
     assert p.grad is not None and p.grad.dtype == torch.bfloat16
     st.finish_backward()
     i = next(i for i, q in enumerate(st.params) if q is p)
