@@ -17,7 +17,7 @@ DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
 EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba1_bwd_chunk_tokens", "dm_mamba2_ssd_fwd", "dm_mamba2_ssd_bwd", "dm_merge_directions_multi", "dm_spiral_pre", "dm_spiral_post_ln",
            "dm_spiral_post_mix", "dm_spiral_post_mix_pre", "dm_spiral_pre_bwd", "dm_spiral_post_mix_bwd", "dm_spiral_post_ln_bwd",
-           "dm_merge_directions", "dm_gemm_bf16_tn", "dm_gemm_bf16_tn_ex", "dm_p_sample_update", "dm_adamw_ema_step", "dm_adamw_ema_step_ex", "dm_version", "dm_status_string", "dm_last_cuda_error",
+           "dm_merge_directions", "dm_gemm_bf16_tn", "dm_gemm_bf16_tn_ex", "dm_p_sample_update", "dm_adamw_ema_step", "dm_adamw_ema_step_ex", "dm_spiral_post_mix_fold", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
 
@@ -87,6 +87,18 @@ class Mamba2Args(C.Structure):
         ("act_dtype", C.c_int32), ("out_order", C.c_int32), ("n_groups", C.c_int32), ("gate", C.c_int32),
         ("order", C.c_void_p),
         ("group", Mamba2Group * DM_MAX_GROUPS),
+    ]
+
+
+class SpiralFoldArgs(C.Structure):
+    """dm_spiral_fold_args (include/diffma_b200.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("skip", C.c_void_p), ("ab", C.c_void_p), ("g2", C.c_void_p), ("g2_dtype", C.c_int32),
+        ("act_dtype", C.c_int32), ("colsum", C.c_void_p), ("cvec", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
+        ("mod", C.c_void_p), ("mod_batch_stride", C.c_int64), ("x_out", C.c_void_p), ("skip_next", C.c_void_p),
+        ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p), ("mod_next", C.c_void_p), ("mod_next_batch_stride", C.c_int64),
+        ("w", C.c_void_p), ("out2", C.c_void_p), ("batch", C.c_int32), ("seqlen", C.c_int32), ("d_model", C.c_int32),
+        ("eps", C.c_float), ("ln2_eps", C.c_float),
     ]
 
 
@@ -165,6 +177,8 @@ def lib() -> C.CDLL:
     L.dm_adamw_ema_step.restype = C.c_int
     f64 = C.c_double
     L.dm_adamw_ema_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, f64, f64, vp]
+    L.dm_spiral_post_mix_fold.restype = C.c_int
+    L.dm_spiral_post_mix_fold.argtypes = [C.POINTER(SpiralFoldArgs), vp]
     L.dm_adamw_ema_step_ex.restype = C.c_int
     L.dm_adamw_ema_step_ex.argtypes = [C.POINTER(AdamwArgs), vp]
     if L.dm_version() != DM_ABI_VERSION:

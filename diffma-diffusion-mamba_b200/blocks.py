@@ -24,6 +24,7 @@ from .mixer import Mamba, Mamba2, mix_groups
 # persistent 128x256 one-CTA tiles; measured r02 (profiles/r02_notes.md): 19.2 vs 14.2 us (in), 19.8 vs 15.5 us (out,
 # even with 3x fewer flops), 9.0 vs 5.6 us (attention Linear) -- and the scan's gain from the hoisted gate (131 -> 125 us)
 # does not pay for the difference.
+_LN_FOLD = os.environ.get("DIFFMA_LN_FOLD", "1") != "0"     # inference: attention LayerNorm folded around its Linear
 _USE_TCGEN05_GEMM = os.environ.get("DIFFMA_GEMM", "cublas") == "tcgen05"
 # DIFFMA_FUSED_TRAIN=0: differentiate the block glue op by op with torch autograd (the module path below) instead of the
 # fused row kernels + their hand-written adjoints (A/B runs and the gradient parity tests)
@@ -129,6 +130,16 @@ class Spiral_MambaBlock(nn.Module):
             "ln2": (self.attention_network[0].weight.detach().float().contiguous(),
                     self.attention_network[0].bias.detach().float().contiguous()),
         }
+        # attention LayerNorm folded around attention_network[1] (dm_spiral_post_mix_fold): W' = W * gamma in the act dtype,
+        # split into the a- and b-halves of its input; colsum from the ROUNDED W' (what the GEMM multiplies by)
+        with torch.no_grad():
+            an = self.attention_network
+            Dm = an[1].weight.shape[0]
+            wf = (an[1].weight.float() * an[0].weight.float()[None, :]).to(act)                    # (D, 2D)
+            cache["att_wf"] = torch.stack([wf[:, :Dm].t(), wf[:, Dm:].t()]).contiguous()           # (2, K = D, N = D)
+            cache["att_colsum"] = wf.float().sum(1).contiguous()
+            cache["att_cvec"] = (an[1].weight.float() @ an[0].bias.float() + an[1].bias.float()).contiguous()
+            cache["ln2_eps"] = float(an[0].eps)
         self._fcache = cache
         return cache
 
@@ -157,7 +168,21 @@ class Spiral_MambaBlock(nn.Module):
             wrow = None if w is None else w.reshape(B * L).float().contiguous()
             x2 = ops.spiral_pre(x, skip, W["ln1"][0], W["ln1"][1], mod, wrow, act)            # (2, B*L, D)
             ab, hidden = self._fused_core(x2, B, L, act)
+            return self._post_mix(x, skip, ab, hidden, W, mod)
+
+    def _post_mix(self, x, skip, ab, hidden, W, mod, pre=None):
+        """Close the block: sigmoid mix + gated residual [+ the next block's / final layer's LN + modulate, ``pre`` =
+        (skip_next, ln_weight, ln_bias, mod_next, w, eps)].  ``hidden`` is what ``_fused_core`` returned: the attention
+        Linear's output, or -- LayerNorm folded (``_LN_FOLD``) -- the pair of raw products (2, B*L, D)."""
+        from . import ops
+        if hidden.dim() == 3:
+            return ops.spiral_post_mix_fold(x, skip, ab, hidden, W["att_colsum"], W["att_cvec"], W["ln2_eps"], W["w3"],
+                                            W["b3"], mod, pre=pre)
+        if pre is None:
             return ops.spiral_post_mix(x, skip, ab, hidden, W["w3"], W["b3"], mod)
+        skip_next, ln_w, ln_b, mod_next, w, eps = pre
+        return ops.spiral_post_mix_pre(x, skip, ab, hidden, W["w3"], W["b3"], mod, skip_next, ln_w, ln_b, mod_next, w,
+                                       eps=eps)
 
     def _fused_core(self, x2, B, L, act):
         """The part of the block between the two row kernels: in_proj GEMM -> all directions of both mixers (one scan
@@ -202,6 +227,10 @@ class Spiral_MambaBlock(nn.Module):
                 o = torch.bmm(v.view(2, B * L * K, -1), self._m2_out_weights(act))               # (2, B*L*K, D)
                 rstd = torch.rsqrt(ss / m1.d_inner + m1.norm.eps).transpose(2, 3)                # (2, B, L, K)
                 ab = (o.view(2, B * L, K, D) * rstd.reshape(2, B * L, K, 1).to(act)).sum(2)
+            if _LN_FOLD and not tc:
+                # LayerNorm folded around the Linear: two K = D products on the raw a, b (fp32 out: the row kernel subtracts
+                # mean * colsum from them); the row kernel that follows supplies mean / rstd
+                return ab, torch.bmm(ab, W["att_wf"], out_dtype=torch.float32) if act != torch.float32 else torch.bmm(ab, W["att_wf"])
             lnab = ops.spiral_post_ln(ab, W["ln2"][0], W["ln2"][1])                              # (B*L, 2D)
             if tc:
                 hidden = ops.gemm_bf16_tn(lnab.unsqueeze(0), W["att_w"].unsqueeze(0), bias=W["att_b32"])[0]

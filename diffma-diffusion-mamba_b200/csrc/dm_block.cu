@@ -7,6 +7,8 @@
 //   post_mix alpha = sigmoid(w3 . silu(hidden) + b3) ; x_new = (x + skip) + gate * (alpha a + (1-alpha) b)
 //                                                                              (lines 111-114)
 // The reference runs ~35 elementwise / reduction launches for the same work.
+#include <type_traits>
+
 #include "dm_common.cuh"
 
 namespace dm {
@@ -157,34 +159,86 @@ spiral_post_ln_kernel(const T* __restrict__ ab, const float* __restrict__ ln_w, 
         }
 }
 
-template <typename T, int NV>
+// alpha = sigmoid(w3 . silu(hidden) + b3) of one token row (reference block/mamba_block.py:110-112), and the row's a / b
+// values for the mix that follows.
+//   kFold = false: `hidden` = Linear(LN(cat(a, b))) as computed by spiral_post_ln + a GEMM.
+//   kFold = true : the LayerNorm is folded around the GEMM.  With W' = W * gamma (per input column), colsum[n] = sum_k W'[n][k]
+//                  and cvec[n] = sum_k beta[k] W[n][k] + bias[n]:
+//                      Linear(LN(x))[n] = rstd * (x . W'[n] - mean * colsum[n]) + cvec[n]
+//                  so the GEMM runs on the raw cat(a, b) -- as two K = D products g2[0] = a W'_a^T, g2[1] = b W'_b^T -- and
+//                  this kernel, which reads a and b anyway, supplies mean and rstd.  One launch and one (rows, 2D) round
+//                  trip less per block than spiral_post_ln + GEMM.
+template <typename T, typename TH, int NV, bool kFold>
+__device__ __forceinline__ float mix_alpha(const T* __restrict__ ab, const TH* __restrict__ hidden, const float* __restrict__ w3,
+                                           const float* __restrict__ b3, const float* __restrict__ colsum,
+                                           const float* __restrict__ cvec, float eps2, int rows, int row, int lane,
+                                           float (&av)[NV][8], float (&bv)[NV][8]) {
+    constexpr int D = NV * 256;
+    float mean = 0.f, rstd = 1.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int64_t off = static_cast<int64_t>(row) * D + (i * 32 + lane) * 8;
+        V8<T>::load(ab + off, av[i]);
+        V8<T>::load(ab + static_cast<int64_t>(rows) * D + off, bv[i]);
+    }
+    if constexpr (kFold) {
+        float sm = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sm += av[i][e] + bv[i][e];
+        mean = warp_sum(sm) * (0.5f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float da = av[i][e] - mean, db = bv[i][e] - mean;
+                q = fmaf(da, da, fmaf(db, db, q));
+            }
+        rstd = rsqrtf(warp_sum(q) * (0.5f / D) + eps2);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        float hv[8], wv[8];
+        V8<TH>::load(hidden + static_cast<int64_t>(row) * D + c, hv);
+        V8<float>::load(w3 + c, wv);
+        if constexpr (kFold) {
+            float h1[8], cs[8], cv[8];
+            V8<TH>::load(hidden + (static_cast<int64_t>(rows) + row) * D + c, h1);
+            V8<float>::load(colsum + c, cs);
+            V8<float>::load(cvec + c, cv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hv[e] = fmaf(rstd, fmaf(-mean, cs[e], hv[e] + h1[e]), cv[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s = fmaf(silu_fast(hv[e]), wv[e], s);
+    }
+    return sigmoid_fast(warp_sum(s) + __ldg(b3));
+}
+
+template <typename T, int NV, typename TH = T, bool kFold = false>
 __global__ void __launch_bounds__(kRowWarps * 32)
 spiral_post_mix_kernel(const float* __restrict__ x, const float* __restrict__ skip, const T* __restrict__ ab,
-                       const T* __restrict__ hidden, const float* __restrict__ w3, const float* __restrict__ b3,
-                       const float* __restrict__ mod, int64_t mod_stride, float* __restrict__ out, int rows, int L) {
+                       const TH* __restrict__ hidden, const float* __restrict__ w3, const float* __restrict__ b3,
+                       const float* __restrict__ mod, int64_t mod_stride, float* __restrict__ out, int rows, int L,
+                       const float* __restrict__ colsum, const float* __restrict__ cvec, float eps2) {
     constexpr int D = NV * 256;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
     pdl_wait();                                 // (PDL: the predecessor's writes are visible from here on)
     const int b = row / L;
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        float hv[8], wv[8];
-        V8<T>::load(hidden + static_cast<int64_t>(row) * D + c, hv);
-        V8<float>::load(w3 + c, wv);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) s = fmaf(silu_fast(hv[e]), wv[e], s);
-    }
-    const float alpha = sigmoid_fast(warp_sum(s) + __ldg(b3));
+    float av[NV][8], bv[NV][8];
+    const float alpha = mix_alpha<T, TH, NV, kFold>(ab, hidden, w3, b3, colsum, cvec, eps2, rows, row, lane, av, bv);
     const float* gate = mod + static_cast<int64_t>(b) * mod_stride + 2 * D;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 8;
         const int64_t off = static_cast<int64_t>(row) * D + c;
-        float xa[8], av[8], bv[8], gv[8], o[8];
+        float xa[8], gv[8], o[8];
         V8<float>::load(x + off, xa);
         if (skip) {
             float t[8];
@@ -192,11 +246,9 @@ spiral_post_mix_kernel(const float* __restrict__ x, const float* __restrict__ sk
 #pragma unroll
             for (int e = 0; e < 8; ++e) xa[e] += t[e];
         }
-        V8<T>::load(ab + off, av);
-        V8<T>::load(ab + static_cast<int64_t>(rows) * D + off, bv);
         V8<float>::load(gate + c, gv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaf(gv[e], fmaf(alpha, av[e] - bv[e], bv[e]), xa[e]);
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(gv[e], fmaf(alpha, av[i][e] - bv[i][e], bv[i][e]), xa[e]);
         V8<float>::store(out + off, o);
     }
 }
@@ -204,31 +256,23 @@ spiral_post_mix_kernel(const float* __restrict__ x, const float* __restrict__ sk
 // post_mix of block i fused with pre of block i+1 (or of the final layer): the new residual row never leaves the
 // registers between the two.  x_out = (x + skip) + gate (alpha a + (1 - alpha) b)   [block i, as spiral_post_mix]
 //                             out2  = modulate(LayerNorm(x_out + skip2)) [, * w]     [block i+1, as spiral_pre]
-template <typename T, int NV>
+template <typename T, int NV, typename TH = T, bool kFold = false>
 __global__ void __launch_bounds__(kRowWarps * 32)
 spiral_post_mix_pre_kernel(const float* __restrict__ x, const float* __restrict__ skip, const T* __restrict__ ab,
-                           const T* __restrict__ hidden, const float* __restrict__ w3, const float* __restrict__ b3,
+                           const TH* __restrict__ hidden, const float* __restrict__ w3, const float* __restrict__ b3,
                            const float* __restrict__ mod, int64_t mod_stride, float* __restrict__ x_out,
                            const float* __restrict__ skip2, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                            const float* __restrict__ mod2, int64_t mod2_stride, const float* __restrict__ w,
-                           T* __restrict__ out2, int rows, int L, float eps) {
+                           T* __restrict__ out2, int rows, int L, float eps, const float* __restrict__ colsum,
+                           const float* __restrict__ cvec, float eps2) {
     constexpr int D = NV * 256;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
     pdl_wait();                                 // (PDL: the predecessor's writes are visible from here on)
     const int b = row / L;
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        float hv[8], wv[8];
-        V8<T>::load(hidden + static_cast<int64_t>(row) * D + c, hv);
-        V8<float>::load(w3 + c, wv);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) s = fmaf(silu_fast(hv[e]), wv[e], s);
-    }
-    const float alpha = sigmoid_fast(warp_sum(s) + __ldg(b3));
+    float av[NV][8], bv[NV][8];
+    const float alpha = mix_alpha<T, TH, NV, kFold>(ab, hidden, w3, b3, colsum, cvec, eps2, rows, row, lane, av, bv);
     const float* gate = mod + static_cast<int64_t>(b) * mod_stride + 2 * D;
     float v[NV][8];
     float sum = 0.f;
@@ -236,7 +280,7 @@ spiral_post_mix_pre_kernel(const float* __restrict__ x, const float* __restrict_
     for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 8;
         const int64_t off = static_cast<int64_t>(row) * D + c;
-        float xa[8], av[8], bv[8], gv[8];
+        float xa[8], gv[8];
         V8<float>::load(x + off, xa);
         if (skip) {
             float t[8];
@@ -244,11 +288,9 @@ spiral_post_mix_pre_kernel(const float* __restrict__ x, const float* __restrict_
 #pragma unroll
             for (int e = 0; e < 8; ++e) xa[e] += t[e];
         }
-        V8<T>::load(ab + off, av);
-        V8<T>::load(ab + static_cast<int64_t>(rows) * D + off, bv);
         V8<float>::load(gate + c, gv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[i][e] = fmaf(gv[e], fmaf(alpha, av[e] - bv[e], bv[e]), xa[e]);
+        for (int e = 0; e < 8; ++e) v[i][e] = fmaf(gv[e], fmaf(alpha, av[i][e] - bv[i][e], bv[i][e]), xa[e]);
         V8<float>::store(x_out + off, v[i]);
         if (skip2) {
             float t[8];
@@ -333,28 +375,63 @@ extern "C" int dm_spiral_post_ln(const void* ab, const float* ln_weight, const f
     return DM_OK;
 }
 
-extern "C" int dm_spiral_post_mix(const float* x, const float* skip, const void* ab, const void* hidden,
-                                  const float* w3, const float* b3, const float* mod, int64_t mod_batch_stride, float* out,
-                                  int32_t batch, int32_t seqlen, int32_t d_model, int32_t act_dtype, void* stream) {
-    if (!x || !ab || !hidden || !w3 || !b3 || !mod || !out || batch <= 0 || seqlen <= 0) return DM_ERR_INVALID_ARG;
+// hidden_dtype < 0: `hidden` is Linear(LN(cat(a, b))) in the activation dtype (the unfused form).  Otherwise `hidden` is the
+// pair of raw products g2 (2, rows, D) in hidden_dtype (DM_F32 or the activation dtype) and colsum / cvec / ln2_eps carry
+// the folded LayerNorm (see mix_alpha).
+static int post_mix_launch(const float* x, const float* skip, const void* ab, const void* hidden, int hidden_dtype,
+                           const float* colsum, const float* cvec, float ln2_eps, const float* w3, const float* b3,
+                           const float* mod, int64_t mod_batch_stride, float* x_out, bool with_pre, const float* skip_next,
+                           const float* ln_weight, const float* ln_bias, const float* mod_next, int64_t mod_next_batch_stride,
+                           const float* w, void* out2, int32_t batch, int32_t seqlen, int32_t d_model, float eps,
+                           int32_t act_dtype, void* stream) {
+    if (!x || !ab || !hidden || !w3 || !b3 || !mod || !x_out || batch <= 0 || seqlen <= 0) return DM_ERR_INVALID_ARG;
+    if (with_pre && (!ln_weight || !ln_bias || !mod_next || !out2)) return DM_ERR_INVALID_ARG;
+    const bool fold = hidden_dtype >= 0;
+    if (fold && (!colsum || !cvec || !aligned16(colsum) || !aligned16(cvec))) return DM_ERR_INVALID_ARG;
     if (d_model != 512) return DM_ERR_UNSUPPORTED;
-    if (!aligned16(x) || !aligned16(ab) || !aligned16(hidden) || !aligned16(out) || !aligned16(mod) ||
+    if (!aligned16(x) || !aligned16(ab) || !aligned16(hidden) || !aligned16(x_out) || !aligned16(mod) ||
         (skip && !aligned16(skip)) || (mod_batch_stride % 4))
         return DM_ERR_INVALID_ARG;
+    if (with_pre && (!aligned16(mod_next) || !aligned16(out2) || (skip_next && !aligned16(skip_next)) || (mod_next_batch_stride % 4)))
+        return DM_ERR_INVALID_ARG;
+    if (act_dtype != DM_BF16 && act_dtype != DM_F32) return DM_ERR_UNSUPPORTED;
+    if (fold && hidden_dtype != DM_F32 && hidden_dtype != act_dtype) return DM_ERR_UNSUPPORTED;
     const int rows = batch * seqlen;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (act_dtype == DM_BF16)
-        launch_pdl(kPdlRow, spiral_post_mix_kernel<__nv_bfloat16, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, x, skip, static_cast<const __nv_bfloat16*>(ab), static_cast<const __nv_bfloat16*>(hidden), w3, b3, mod,
-            mod_batch_stride, out, rows, seqlen);
-    else if (act_dtype == DM_F32)
-        launch_pdl(kPdlRow, spiral_post_mix_kernel<float, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, x, skip, static_cast<const float*>(ab), static_cast<const float*>(hidden), w3, b3, mod, mod_batch_stride,
-            out, rows, seqlen);
-    else
-        return DM_ERR_UNSUPPORTED;
+    const dim3 grid(row_grid(rows)), block(kRowWarps * 32);
+    auto go = [&](auto tag_t, auto tag_h, auto tag_fold) -> cudaError_t {
+        using T = decltype(tag_t);
+        using TH = decltype(tag_h);
+        constexpr bool kF = decltype(tag_fold)::value;
+        if (with_pre)
+            return launch_pdl(kPdlRow, spiral_post_mix_pre_kernel<T, 2, TH, kF>, grid, block, 0, st, x, skip,
+                              static_cast<const T*>(ab), static_cast<const TH*>(hidden), w3, b3, mod, mod_batch_stride, x_out,
+                              skip_next, ln_weight, ln_bias, mod_next, mod_next_batch_stride, w, static_cast<T*>(out2), rows,
+                              seqlen, eps, colsum, cvec, ln2_eps);
+        return launch_pdl(kPdlRow, spiral_post_mix_kernel<T, 2, TH, kF>, grid, block, 0, st, x, skip, static_cast<const T*>(ab),
+                          static_cast<const TH*>(hidden), w3, b3, mod, mod_batch_stride, x_out, rows, seqlen, colsum, cvec,
+                          ln2_eps);
+    };
+    cudaError_t e;
+    if (act_dtype == DM_BF16) {
+        if (!fold) e = go(__nv_bfloat16{}, __nv_bfloat16{}, std::false_type{});
+        else if (hidden_dtype == DM_F32) e = go(__nv_bfloat16{}, float{}, std::true_type{});
+        else e = go(__nv_bfloat16{}, __nv_bfloat16{}, std::true_type{});
+    } else {
+        if (!fold) e = go(float{}, float{}, std::false_type{});
+        else e = go(float{}, float{}, std::true_type{});
+    }
+    DM_CUDA_TRY(e);
     DM_CUDA_TRY(cudaGetLastError());
     return DM_OK;
 }
 
+extern "C" int dm_spiral_post_mix(const float* x, const float* skip, const void* ab, const void* hidden,
+                                  const float* w3, const float* b3, const float* mod, int64_t mod_batch_stride, float* out,
+                                  int32_t batch, int32_t seqlen, int32_t d_model, int32_t act_dtype, void* stream) {
+    return post_mix_launch(x, skip, ab, hidden, -1, nullptr, nullptr, 0.f, w3, b3, mod, mod_batch_stride, out, false, nullptr,
+                           nullptr, nullptr, nullptr, 0, nullptr, nullptr, batch, seqlen, d_model, 0.f, act_dtype, stream);
+}
 
 extern "C" int dm_spiral_post_mix_pre(const float* x, const float* skip, const void* ab, const void* hidden,
                                       const float* w3, const float* b3, const float* mod, int64_t mod_batch_stride,
@@ -362,27 +439,18 @@ extern "C" int dm_spiral_post_mix_pre(const float* x, const float* skip, const v
                                       const float* mod_next, int64_t mod_next_batch_stride, const float* w, void* out2,
                                       int32_t batch, int32_t seqlen, int32_t d_model, float eps, int32_t act_dtype,
                                       void* stream) {
-    if (!x || !ab || !hidden || !w3 || !b3 || !mod || !x_out || !ln_weight || !ln_bias || !mod_next || !out2 || batch <= 0 ||
-        seqlen <= 0)
-        return DM_ERR_INVALID_ARG;
-    if (d_model != 512) return DM_ERR_UNSUPPORTED;
-    if (!aligned16(x) || !aligned16(ab) || !aligned16(hidden) || !aligned16(x_out) || !aligned16(mod) || !aligned16(mod_next) ||
-        !aligned16(out2) || (skip && !aligned16(skip)) || (skip_next && !aligned16(skip_next)) || (mod_batch_stride % 4) ||
-        (mod_next_batch_stride % 4))
-        return DM_ERR_INVALID_ARG;
-    const int rows = batch * seqlen;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (act_dtype == DM_BF16)
-        launch_pdl(kPdlRow, spiral_post_mix_pre_kernel<__nv_bfloat16, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, x, skip, static_cast<const __nv_bfloat16*>(ab), static_cast<const __nv_bfloat16*>(hidden), w3, b3, mod,
-            mod_batch_stride, x_out, skip_next, ln_weight, ln_bias, mod_next, mod_next_batch_stride, w,
-            static_cast<__nv_bfloat16*>(out2), rows, seqlen, eps);
-    else if (act_dtype == DM_F32)
-        launch_pdl(kPdlRow, spiral_post_mix_pre_kernel<float, 2>, dim3(row_grid(rows)), dim3(kRowWarps * 32), 0, st, x, skip, static_cast<const float*>(ab), static_cast<const float*>(hidden), w3, b3, mod, mod_batch_stride, x_out,
-            skip_next, ln_weight, ln_bias, mod_next, mod_next_batch_stride, w, static_cast<float*>(out2), rows, seqlen, eps);
-    else
-        return DM_ERR_UNSUPPORTED;
-    DM_CUDA_TRY(cudaGetLastError());
-    return DM_OK;
+    return post_mix_launch(x, skip, ab, hidden, -1, nullptr, nullptr, 0.f, w3, b3, mod, mod_batch_stride, x_out, true, skip_next,
+                           ln_weight, ln_bias, mod_next, mod_next_batch_stride, w, out2, batch, seqlen, d_model, eps, act_dtype,
+                           stream);
+}
+
+extern "C" int dm_spiral_post_mix_fold(const dm_spiral_fold_args* a, void* stream) {
+    if (!a) return DM_ERR_INVALID_ARG;
+    if (a->g2_dtype != DM_F32 && a->g2_dtype != DM_BF16) return DM_ERR_UNSUPPORTED;
+    return post_mix_launch(a->x, a->skip, a->ab, a->g2, a->g2_dtype, a->colsum, a->cvec, a->ln2_eps, a->w3, a->b3, a->mod,
+                           a->mod_batch_stride, a->x_out, a->out2 != nullptr, a->skip_next, a->ln_weight, a->ln_bias,
+                           a->mod_next, a->mod_next_batch_stride, a->w, a->out2, a->batch, a->seqlen, a->d_model, a->eps,
+                           a->act_dtype, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------

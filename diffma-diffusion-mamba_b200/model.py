@@ -248,12 +248,11 @@ class DiffMa(nn.Module):
                     j = i + 1
                     skip_next = outs[self.depth - j - 1] if (j > self.depth / 2) else None
                     Wn = self.blocks[j]._fused_weights(act)
-                    h, x2 = ops.spiral_post_mix_pre(h, skip, ab, hidden, Wb["w3"], Wb["b3"], mods[:, i], skip_next,
-                                                    Wn["ln1"][0], Wn["ln1"][1], mods[:, j], wrow)
+                    h, x2 = blk._post_mix(h, skip, ab, hidden, Wb, mods[:, i],
+                                          pre=(skip_next, Wn["ln1"][0], Wn["ln1"][1], mods[:, j], wrow, 1e-5))
                     skip = skip_next
                 else:
-                    h, x2 = ops.spiral_post_mix_pre(h, skip, ab, hidden, Wb["w3"], Wb["b3"], mods[:, i], None,
-                                                    ones, zeros, fmod, None, eps=1e-6)
+                    h, x2 = blk._post_mix(h, skip, ab, hidden, Wb, mods[:, i], pre=(None, ones, zeros, fmod, None, 1e-6))
                 outs.append(h)
             hn = x2[0].view(h.shape)
             with torch.autocast("cuda", enabled=False):

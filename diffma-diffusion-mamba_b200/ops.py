@@ -600,6 +600,38 @@ def spiral_post_mix_pre(x, skip, ab, hidden, w3, b3, mod, skip_next, ln_weight, 
     return x_out, out2
 
 
+def spiral_post_mix_fold(x, skip, ab, g2, colsum, cvec, ln2_eps, w3, b3, mod, pre=None):
+    """``spiral_post_mix`` / ``spiral_post_mix_pre`` with the attention network's LayerNorm folded around its Linear
+    (``dm_spiral_post_mix_fold``): ``g2`` (2, B*L, D) holds the raw products a W'_a^T, b W'_b^T (fp32 or ab's dtype), the
+    kernel derives mean / rstd of cat(a, b) from the rows it reads anyway.  ``pre`` = None, or (skip_next, ln_weight,
+    ln_bias, mod_next, w, eps) to open the next block in the same launch.  Returns x_new, or (x_new, out2)."""
+    B, L, D = x.shape
+    if not (ab.is_contiguous() and g2.is_contiguous() and tuple(g2.shape) == tuple(ab.shape) == (2, B * L, D)):
+        raise RuntimeError("spiral_post_mix_fold: ab / g2 must be contiguous (2, B*L, D)")
+    if g2.dtype not in (torch.float32, ab.dtype):
+        raise TypeError("spiral_post_mix_fold: g2 must be fp32 or of ab's dtype")
+    x_out = torch.empty_like(x)
+    a = _cabi.SpiralFoldArgs()
+    a.x, a.skip = _f32c(x, "x").data_ptr(), None if skip is None else _f32c(skip, "skip").data_ptr()
+    a.ab, a.g2, a.g2_dtype, a.act_dtype = ab.data_ptr(), g2.data_ptr(), _dtype_code(g2), _dtype_code(ab)
+    a.colsum, a.cvec = _f32c(colsum, "colsum").data_ptr(), _f32c(cvec, "cvec").data_ptr()
+    a.w3, a.b3 = _f32c(w3, "w3").data_ptr(), _f32c(b3, "b3").data_ptr()
+    a.mod, a.mod_batch_stride, a.x_out = _mod2d(mod).data_ptr(), mod.stride(0), x_out.data_ptr()
+    a.batch, a.seqlen, a.d_model, a.ln2_eps = B, L, D, ln2_eps
+    out2 = None
+    if pre is not None:
+        skip_next, ln_weight, ln_bias, mod_next, w, eps = pre
+        out2 = torch.empty((2, B * L, D), dtype=ab.dtype, device=x.device)
+        a.skip_next = None if skip_next is None else _f32c(skip_next, "skip_next").data_ptr()
+        a.ln_weight, a.ln_bias = _f32c(ln_weight, "ln_weight").data_ptr(), _f32c(ln_bias, "ln_bias").data_ptr()
+        a.mod_next, a.mod_next_batch_stride = _mod2d(mod_next).data_ptr(), mod_next.stride(0)
+        a.w, a.out2, a.eps = None if w is None else _f32c(w, "w").data_ptr(), out2.data_ptr(), eps
+    st = _cabi.lib().dm_spiral_post_mix_fold(C.byref(a), _stream_handle(x.device))
+    _cabi.check(st, "dm_spiral_post_mix_fold")
+    LAUNCH_COUNTER["kernels"] += 1
+    return x_out if pre is None else (x_out, out2)
+
+
 def _mod2d(mod: torch.Tensor) -> torch.Tensor:
     """adaLN output (B, 3D) fp32, rows may be strided (a slice of the all-blocks GEMM), channels contiguous."""
     if mod.dtype != torch.float32 or mod.dim() != 2 or mod.stride(1) != 1 or not mod.is_cuda or mod.stride(0) % 4:

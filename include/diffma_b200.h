@@ -243,6 +243,31 @@ int dm_spiral_post_mix_pre(const float* x, const float* skip, const void* ab, co
                            int64_t mod_next_batch_stride, const float* w, void* out2, int32_t batch, int32_t seqlen,
                            int32_t d_model, float eps, int32_t act_dtype, void* stream);
 
+/* The same two operations with the attention network's LayerNorm FOLDED around its Linear (reference
+ * block/mamba_block.py:110: attention_network = LayerNorm(2D) -> Linear(2D, D) -> SiLU -> Linear(D, 1) -> Sigmoid):
+ *     Linear(LN(cat(a, b)))[n] = rstd * (a . W'_a[n] + b . W'_b[n] - mean * colsum[n]) + cvec[n],
+ *     W' = W * gamma (per input column), colsum[n] = sum_k W'[n][k], cvec[n] = sum_k beta[k] W[n][k] + bias[n],
+ * so the caller runs the GEMM on the raw out-projection results -- g2[0] = a W'_a^T, g2[1] = b W'_b^T, (2, rows, D), fp32 or
+ * the activation dtype -- and this kernel, which reads a and b anyway, supplies the row's mean and rstd: dm_spiral_post_ln and
+ * its (rows, 2D) round trip disappear.  out2 == NULL: plain post_mix (writes x_out only); otherwise post_mix + pre of the
+ * next block as dm_spiral_post_mix_pre.  Inference only (no adjoint is provided for this form). */
+typedef struct dm_spiral_fold_args {
+    const float* x; const float* skip;        /* (B, L, D) fp32; skip may be NULL                                      */
+    const void* ab;                           /* (2, B*L, D) activation dtype                                          */
+    const void* g2; int32_t g2_dtype;         /* (2, B*L, D); DM_F32 or the activation dtype                           */
+    int32_t act_dtype;
+    const float* colsum; const float* cvec;   /* (D) fp32 each                                                         */
+    const float* w3; const float* b3;         /* attention_network[3]: (D), (1) fp32                                   */
+    const float* mod; int64_t mod_batch_stride;
+    float* x_out;
+    const float* skip_next; const float* ln_weight; const float* ln_bias;        /* pre part, as dm_spiral_post_mix_pre */
+    const float* mod_next; int64_t mod_next_batch_stride; const float* w;
+    void* out2;                               /* NULL: no pre part                                                     */
+    int32_t batch, seqlen, d_model;
+    float eps, ln2_eps;                       /* eps of the next block's LayerNorm / of the attention LayerNorm        */
+} dm_spiral_fold_args;
+int dm_spiral_post_mix_fold(const dm_spiral_fold_args* args, void* stream);
+
 /* Adjoints of the three row kernels above for the training step (autograd of block/mamba_block.py:100-115, reached from
  * train.py:259).  Per-batch-element and per-parameter gradients are ACCUMULATED (atomics) into buffers the caller zeroed:
  *   dm_spiral_pre_bwd       d_out2 (2, rows, d) act dtype -> dx (rows, d) fp32 [= d skip]; d_mod[:, 0:d] += d shift,

@@ -32,6 +32,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_cabi.GemmArgs) == 13 * 8 + 6 * 4                                              # 104 + 24 = 128
     assert ctypes.sizeof(_cabi.Mamba2Group) == 15 * 8
     assert ctypes.sizeof(_cabi.AdamwArgs) == 8 * 8 + 7 * 8                                               # ABI 6
+    assert ctypes.sizeof(_cabi.SpiralFoldArgs) == 176                                                   # ABI 6
     assert ctypes.sizeof(_cabi.Mamba2Args) == 11 * 4 + 4 + 8 + 4 * ctypes.sizeof(_cabi.Mamba2Group)
 
 

@@ -190,12 +190,73 @@ def test_errors_are_loud(dev):
                            p["D"].to(dev), delta_bias=p["dt_bias"].to(dev))
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("with_pre", [False, True])
+def test_folded_attention_layernorm_equals_post_ln_plus_linear(dev, dtype, with_pre):
+    """dm_spiral_post_mix_fold (LayerNorm(cat(a, b)) folded around attention_network[1]; the GEMM runs on the raw a, b) vs
+    dm_spiral_post_ln -> Linear -> dm_spiral_post_mix[_pre], on rows with a large common offset (the folded form subtracts
+    mean * colsum from the products: the offset is what could cancel badly) and rows past a multiple of the warp count."""
+    from diffma_b200 import ops
+    act = torch.float32 if dtype == "fp32" else torch.bfloat16
+    g = torch.Generator().manual_seed(3)
+    B, L, D = 3, 37, 512
+    rows = B * L
+    x = torch.randn(B, L, D, generator=g).to(dev)
+    skip = torch.randn(B, L, D, generator=g).to(dev)
+    off = torch.randn(rows, 1, generator=g) * 3.0                       # per-row mean up to ~3 sigma of the features
+    ab = (torch.randn(2, rows, D, generator=g) + off[None]).to(dev).to(act)
+    gamma = (1.0 + 0.2 * torch.randn(2 * D, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(2 * D, generator=g)).to(dev)
+    W = (torch.randn(D, 2 * D, generator=g) / (2 * D) ** 0.5).to(dev)
+    bias = (0.1 * torch.randn(D, generator=g)).to(dev)
+    w3 = (torch.randn(D, generator=g) / D ** 0.5).to(dev)
+    b3 = torch.randn(1, generator=g).to(dev)
+    mod = torch.randn(B, 3 * D, generator=g).to(dev)
+    mod2 = torch.randn(B, 3 * D, generator=g).to(dev)
+    lnw, lnb = (1.0 + 0.1 * torch.randn(D, generator=g)).to(dev), (0.1 * torch.randn(D, generator=g)).to(dev)
+    wrow = torch.rand(rows, generator=g).to(dev)
+    eps2 = 1e-5
+    # unfused: LN -> Linear (weights in the act dtype, as the block caches them) -> post_mix[_pre]
+    lnab = ops.spiral_post_ln(ab, gamma, beta)
+    hidden = torch.nn.functional.linear(lnab, W.to(act), bias.to(act))
+    # folded
+    wf = (W * gamma[None, :]).to(act)
+    g2 = torch.bmm(ab, torch.stack([wf[:, :D].t(), wf[:, D:].t()]).contiguous(),
+                   **({} if act == torch.float32 else dict(out_dtype=torch.float32)))
+    colsum, cvec = wf.float().sum(1).contiguous(), (W @ beta + bias).contiguous()
+    if with_pre:
+        pre = (skip, lnw, lnb, mod2, wrow, 1e-5)
+        ref_x, ref_o = ops.spiral_post_mix_pre(x, skip, ab, hidden, w3, b3, mod, skip, lnw, lnb, mod2, wrow)
+        got_x, got_o = ops.spiral_post_mix_fold(x, skip, ab, g2, colsum, cvec, eps2, w3, b3, mod, pre=pre)
+    else:
+        ref_x = ops.spiral_post_mix(x, skip, ab, hidden, w3, b3, mod)
+        got_x = ops.spiral_post_mix_fold(x, skip, ab, g2, colsum, cvec, eps2, w3, b3, mod)
+    # fp32: TF32-free GEMMs on both sides would agree to 1e-5; torch's default fp32 matmul here is exact fp32 as well.
+    # bf16: `hidden` is rounded to bf16 on the unfused side (2^-9 relative) and not on the folded one
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == "fp32" else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(got_x, ref_x, **tol)
+    if with_pre:
+        torch.testing.assert_close(got_o.float(), ref_o.float(), **(tol if dtype == "fp32" else dict(rtol=3e-2, atol=3e-2)))
+    # and the alpha the two forms imply agrees much tighter than the mixed output shows: compare through a pure-torch fp64 LN
+    x64 = torch.cat([ab[0], ab[1]], 1).double()
+    ln64 = torch.nn.functional.layer_norm(x64, (2 * D,), gamma.double(), beta.double(), eps2)
+    h64 = ln64 @ W.double().t() + bias.double()
+    alpha64 = torch.sigmoid(torch.nn.functional.silu(h64) @ w3.double() + b3.double())
+    gate = mod[:, 2 * D:].double().repeat_interleave(L, 0)
+    want = (x + skip).double().view(rows, D) + gate * (alpha64[:, None] * ab[0].double() + (1 - alpha64[:, None]) * ab[1].double())
+    err_fold = (got_x.double().view(rows, D) - want).abs().max()
+    err_ref = (ref_x.double().view(rows, D) - want).abs().max()
+    assert float(err_fold) <= max(2.0 * float(err_ref), 1e-4 if dtype == "fp32" else 2e-2)
+
+
 @pytest.mark.parametrize("use_m2", [False, True])
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_fused_block_path_equals_module_path(dev, use_m2, dtype):
+@pytest.mark.parametrize("fold", [True, False])
+def test_fused_block_path_equals_module_path(dev, use_m2, dtype, fold, monkeypatch):
     """The 8-launch inference path of Spiral_MambaBlock (dm_spiral_pre / post_ln / post_mix + batched GEMMs) vs the
     module-by-module path (the one autograd uses) on the same weights, incl. the long-skip add."""
-    from diffma_b200 import model as M, synth
+    from diffma_b200 import blocks, model as M, synth
+    monkeypatch.setattr(blocks, "_LN_FOLD", fold)      # attention LayerNorm folded around its Linear, or post_ln + Linear
     torch.manual_seed(0)
     net = M.DiffMa_models["DiffMa-S/2"](input_size=28, dt_rank=16, d_state=16, use_mamba2=use_m2).eval()
     synth.fill_trained_like_(net, seed=11)
