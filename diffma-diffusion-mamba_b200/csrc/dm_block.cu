@@ -454,6 +454,105 @@ extern "C" int dm_spiral_post_mix_fold(const dm_spiral_fold_args* a, void* strea
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Head of DiffMa.forward in one launch (reference model.py:264-281):
+//   h = PatchEmbed(x) + pos_embed        conv with kernel = stride = patch  ==  (C p p) -> D matvec per token
+//   c = cat(t_emb[t] + y, t_emb[t] + mean_T(y2));  the adaLN Linears all consume silu(c): emitted directly, act dtype
+// CTAs [0, n_tok_ctas): 16 tokens each, 256 threads x 2 output columns, the patch pixels gathered from NCHW into shared
+// memory, W (J, D) streamed through L2 (32 KB for patch 2).  CTAs [n_tok_ctas, n_tok_ctas + B): one batch row of c each.
+// Replaces: unfold-copy, fp32 SIMT GEMM, bias/pos add, index_select, two adds, cat, silu, cast  (8 launches).
+// ------------------------------------------------------------------------------------------------------
+namespace dm {
+namespace {
+constexpr int kHeadTok = 16;
+template <typename T>
+__global__ void __launch_bounds__(256)
+step_head_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ posb,
+                 float* __restrict__ h, int B, int C, int Himg, int patch, const int64_t* __restrict__ t,
+                 const float* __restrict__ table, int table_rows, const float* __restrict__ y,
+                 const float* __restrict__ y2m, T* __restrict__ sc, int n_tok_ctas) {
+    constexpr int D = 512;
+    extern __shared__ float px[];                       // [kHeadTok][J]
+    const int tid = threadIdx.x;
+    const int g = Himg / patch, L = g * g, J = C * patch * patch;
+    pdl_wait();
+    if (static_cast<int>(blockIdx.x) >= n_tok_ctas) {   // ---- conditioning row ----
+        const int b = blockIdx.x - n_tok_ctas;
+        const int64_t tt = t[b];
+        const bool ok = tt >= 0 && tt < table_rows;     // (an index beyond the table: poison the row instead of reading past it)
+        for (int d = tid; d < D; d += 256) {
+            const float te = ok ? __ldg(table + tt * D + d) : __int_as_float(0x7fc00000);
+            const float c1 = te + __ldg(y + static_cast<int64_t>(b) * D + d);
+            const float c2 = te + __ldg(y2m + static_cast<int64_t>(b) * D + d);
+            sc[static_cast<int64_t>(b) * 2 * D + d] = from_f32<T>(c1 / (1.0f + __expf(-c1)));
+            sc[static_cast<int64_t>(b) * 2 * D + D + d] = from_f32<T>(c2 / (1.0f + __expf(-c2)));
+        }
+        return;
+    }
+    // ---- patch embedding of kHeadTok tokens ----
+    const int tok0 = blockIdx.x * kHeadTok, n_tok = B * L;
+    for (int i = tid; i < kHeadTok * J; i += 256) {
+        const int tk = i / J, j = i - tk * J;
+        const int tok = min(tok0 + tk, n_tok - 1);
+        const int b = tok / L, l = tok - b * L, gy = l / g, gx = l - gy * g;
+        const int ch = j / (patch * patch), r = j - ch * patch * patch, py = r / patch, pxl = r - py * patch;
+        px[i] = __ldg(x + ((static_cast<int64_t>(b) * C + ch) * Himg + gy * patch + py) * Himg + gx * patch + pxl);
+    }
+    __syncthreads();
+    float acc[kHeadTok][2];
+#pragma unroll
+    for (int k = 0; k < kHeadTok; ++k) acc[k][0] = acc[k][1] = 0.f;
+    const float2* w2 = reinterpret_cast<const float2*>(wp) + tid;        // columns 2 tid, 2 tid + 1 of row j
+    for (int j = 0; j < J; ++j) {
+        const float2 w = __ldg(w2 + static_cast<int64_t>(j) * (D / 2));
+#pragma unroll
+        for (int k = 0; k < kHeadTok; ++k) {
+            const float v = px[k * J + j];
+            acc[k][0] = fmaf(v, w.x, acc[k][0]);
+            acc[k][1] = fmaf(v, w.y, acc[k][1]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kHeadTok; ++k) {
+        const int tok = tok0 + k;
+        if (tok < n_tok) {
+            const int l = tok % L;
+            const float2 pb = __ldg(reinterpret_cast<const float2*>(posb + static_cast<int64_t>(l) * D) + tid);
+            reinterpret_cast<float2*>(h + static_cast<int64_t>(tok) * D)[tid] = make_float2(acc[k][0] + pb.x, acc[k][1] + pb.y);
+        }
+    }
+}
+}  // namespace
+}  // namespace dm
+
+extern "C" int dm_step_head(const float* x, const float* patch_weight, const float* pos_bias, float* h, int32_t batch,
+                            int32_t channels, int32_t image_size, int32_t patch, const int64_t* t, const float* t_table,
+                            int32_t table_rows, const float* y, const float* y2_mean, void* silu_c, int32_t d_model,
+                            int32_t act_dtype, void* stream) {
+    if (!x || !patch_weight || !pos_bias || !h || !t || !t_table || !y || !y2_mean || !silu_c || batch <= 0 || channels <= 0 ||
+        image_size <= 0 || patch <= 0 || table_rows <= 0)
+        return DM_ERR_INVALID_ARG;
+    if (d_model != 512 || image_size % patch) return DM_ERR_UNSUPPORTED;
+    if (act_dtype != DM_BF16 && act_dtype != DM_F32) return DM_ERR_UNSUPPORTED;
+    const int g = image_size / patch, J = channels * patch * patch;
+    const size_t smem = static_cast<size_t>(dm::kHeadTok) * J * sizeof(float);
+    if (smem > 48 * 1024) return DM_ERR_UNSUPPORTED;
+    const int n_tok_ctas = (batch * g * g + dm::kHeadTok - 1) / dm::kHeadTok;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (act_dtype == DM_BF16)
+        e = dm::launch_pdl(dm::kPdlRow, dm::step_head_kernel<__nv_bfloat16>, dim3(n_tok_ctas + batch), dim3(256), smem, st, x,
+                           patch_weight, pos_bias, h, batch, channels, image_size, patch, t, t_table, table_rows, y, y2_mean,
+                           static_cast<__nv_bfloat16*>(silu_c), n_tok_ctas);
+    else
+        e = dm::launch_pdl(dm::kPdlRow, dm::step_head_kernel<float>, dim3(n_tok_ctas + batch), dim3(256), smem, st, x,
+                           patch_weight, pos_bias, h, batch, channels, image_size, patch, t, t_table, table_rows, y, y2_mean,
+                           static_cast<float*>(silu_c), n_tok_ctas);
+    DM_CUDA_TRY(e);
+    DM_CUDA_TRY(cudaGetLastError());
+    return DM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // One reverse-diffusion update (reference gaussian_diffusion.py: p_mean_variance :254-332 with LEARNED_RANGE variance
 // and epsilon prediction, p_sample :376-417) as ONE elementwise kernel instead of ~35 tiny launches + 9 table gathers:
 //   eps, v = split(model_out);  logvar = frac*log(beta_t) + (1-frac)*posterior_logvar_t,  frac = (v+1)/2

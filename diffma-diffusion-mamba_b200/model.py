@@ -10,6 +10,7 @@ The reference's own ``model.py`` runs unchanged on top of ``shims/`` as well (IN
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -19,6 +20,8 @@ from . import scan_orders
 from .blocks import (DiTBlock, EfficientVMamba_MambaBlock, Spiral_MambaBlock, ViM_MambaBlock, VMamba_MambaBlock,
                      Zig_MambaBlock, modulate)
 
+
+_STEP_HEAD = os.environ.get("DIFFMA_STEP_HEAD", "1") != "0"     # inference: fused patch embed + conditioning (dm_step_head)
 
 class PatchEmbed(nn.Module):
     def __init__(self, img_size=28, patch_size=2, stride=2, in_chans=4, embed_dim=512, norm_layer=None, flatten=True):
@@ -167,20 +170,20 @@ class DiffMa(nn.Module):
                 slot[name] = (key, build())
         return slot[name][1]
 
-    def _fused_mods(self, c, act):
+    def _fused_mods(self, c, act, silu_c=None):
         """adaLN of EVERY block and of the final layer in one GEMM: c is the same for all of them in a forward (the
         reference recomputes it per block, block/mamba_block.py:101).  Returns blocks (B, depth, 3D) and final (B, 2D),
-        fp32; weights cached in the act dtype."""
+        fp32; weights cached in the act dtype.  ``silu_c``: silu(c) already in the act dtype (``ops.step_head``)."""
         import torch.nn.functional as F
         lins = [blk.adaLN_modulation[1] for blk in self.blocks] + [self.final_layer.adaLN_modulation[1]]
         ps = [p for lin in lins for p in (lin.weight, lin.bias)]
         w, b = self._cached(f"ada_{act}", ps, lambda: (torch.cat([lin.weight for lin in lins]).to(act).contiguous(),
                                                         torch.cat([lin.bias for lin in lins]).to(act).contiguous()))
         with torch.autocast("cuda", enabled=False):
-            mods = F.linear(F.silu(c.float()).to(act), w, b).float()
+            mods = F.linear(F.silu(c.float()).to(act) if silu_c is None else silu_c, w, b).float()
         D = self.pos_embed.shape[-1]
         nb = self.depth * 3 * D
-        return mods[:, :nb].view(c.shape[0], self.depth, 3 * D), mods[:, nb:]
+        return mods[:, :nb].view(mods.shape[0], self.depth, 3 * D), mods[:, nb:]
 
     def _t_embedding(self, t):
         """t_embedder(t) for integer timesteps from a (1000, D) table built once per weights version: the embedder is a
@@ -202,14 +205,28 @@ class DiffMa(nn.Module):
             raise IndexError(f"timestep {int(t.max())} beyond the {rows}-row embedding table; set model.t_table_rows")
         return table.index_select(0, t.long())
 
+    def _patch_tables(self):
+        """(unfolded conv weight (C*p*p, D) fp32, pos_embed + conv bias (L, D) fp32), cached per weights version."""
+        return self._cached("patch", [self.x_embedder.proj.weight, self.x_embedder.proj.bias, self.pos_embed],
+                            lambda: (self.x_embedder.proj.weight.reshape(self.x_embedder.proj.weight.shape[0], -1).t().contiguous().float(),
+                                     (self.pos_embed[0] + self.x_embedder.proj.bias[None, :]).float().contiguous()))
+
+    def _t_table(self):
+        """TimestepEmbedder at the integer steps 0 .. t_table_rows - 1 (see ``_t_embedding``), fp32 (rows, D)."""
+        ps = list(self.t_embedder.parameters())
+        rows = int(getattr(self, "t_table_rows", 1000))
+
+        def build():
+            with torch.autocast("cuda", enabled=False):
+                return self.t_embedder(torch.arange(rows, device=ps[0].device)).float().contiguous()
+        return self._cached(f"temb{rows}", ps, build)
+
     def _embed_patches(self, x):
         """PatchEmbed conv (kernel = stride = patch) as one matmul on unfolded patches + (bias + pos_embed) table."""
         p = self.patch_size
         N, C, H, W = x.shape
         g = H // p
-        wb = self._cached("patch", [self.x_embedder.proj.weight, self.x_embedder.proj.bias, self.pos_embed],
-                          lambda: (self.x_embedder.proj.weight.reshape(self.x_embedder.proj.weight.shape[0], -1).t().contiguous().float(),
-                                   (self.pos_embed[0] + self.x_embedder.proj.bias[None, :]).float().contiguous()))
+        wb = self._patch_tables()
         patches = x.float().view(N, C, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(N, g * g, C * p * p)
         with torch.autocast("cuda", enabled=False):
             return torch.baddbmm(wb[1].unsqueeze(0), patches, wb[0].unsqueeze(0).expand(N, -1, -1))
@@ -222,12 +239,21 @@ class DiffMa(nn.Module):
         if fused:
             from . import ops
             from .mixer import _act_dtype
-            h = self._embed_patches(x)
-            te = self._t_embedding(t)
             y2m = y2 if y2.dim() == 2 else torch.mean(y2, dim=1)
-            c = torch.cat((te + y, te + y2m), dim=1)
-            act = _act_dtype(h)
-            mods, fmod = self._fused_mods(c, act)
+            act = _act_dtype(x)
+            if (_STEP_HEAD and t.dtype == torch.int64 and x.dtype == torch.float32 and x.is_contiguous()
+                    and y.dtype == torch.float32 and y2m.dtype == torch.float32 and x.shape[2] == x.shape[3]
+                    and x.shape[1] * self.patch_size ** 2 * 16 * 4 <= 48 * 1024):
+                # patch embedding + positional table + conditioning vector (timestep table row + y, + pooled y2) + SiLU in one
+                # launch (dm_step_head) instead of eight
+                wb = self._patch_tables()
+                h, sc = ops.step_head(x, wb[0], wb[1], self.patch_size, t, self._t_table(), y.contiguous(), y2m.contiguous(), act)
+                mods, fmod = self._fused_mods(None, act, silu_c=sc)
+            else:
+                h = self._embed_patches(x)
+                te = self._t_embedding(t)
+                c = torch.cat((te + y, te + y2m), dim=1)
+                mods, fmod = self._fused_mods(c, act)
             B, L, D = h.shape
             ones, zeros = self._cached("fl_affine", [self.pos_embed], lambda: (torch.ones(D, device=h.device),
                                                                                torch.zeros(D, device=h.device)))

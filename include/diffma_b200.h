@@ -268,6 +268,17 @@ typedef struct dm_spiral_fold_args {
 } dm_spiral_fold_args;
 int dm_spiral_post_mix_fold(const dm_spiral_fold_args* args, void* stream);
 
+/* Head of DiffMa.forward in one launch (reference model.py:264-281, visionEmbedding / PatchEmbed, TimestepEmbedder):
+ *   h (B, L, D) fp32        = PatchEmbed(x) + pos_embed: x (B, C, S, S) fp32, patch_weight (C*p*p, D) fp32 (the conv weight
+ *                             unfolded and transposed), pos_bias (L, D) fp32 = pos_embed + conv bias
+ *   silu_c (B, 2D) act dtype = silu(cat(t_table[t] + y, t_table[t] + y2_mean)): what every adaLN Linear consumes; t_table
+ *                             (table_rows, D) fp32 = TimestepEmbedder evaluated at the integer steps, t int64 (a step outside
+ *                             the table poisons its row with NaN), y / y2_mean (B, D) fp32.
+ * D = 512. */
+int dm_step_head(const float* x, const float* patch_weight, const float* pos_bias, float* h, int32_t batch, int32_t channels,
+                 int32_t image_size, int32_t patch, const int64_t* t, const float* t_table, int32_t table_rows, const float* y,
+                 const float* y2_mean, void* silu_c, int32_t d_model, int32_t act_dtype, void* stream);
+
 /* Adjoints of the three row kernels above for the training step (autograd of block/mamba_block.py:100-115, reached from
  * train.py:259).  Per-batch-element and per-parameter gradients are ACCUMULATED (atomics) into buffers the caller zeroed:
  *   dm_spiral_pre_bwd       d_out2 (2, rows, d) act dtype -> dx (rows, d) fp32 [= d skip]; d_mod[:, 0:d] += d shift,

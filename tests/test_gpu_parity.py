@@ -190,6 +190,36 @@ def test_errors_are_loud(dev):
                            p["D"].to(dev), delta_bias=p["dt_bias"].to(dev))
 
 
+@pytest.mark.parametrize("tag,dtype", [("DiffMa-S/2", "bf16"), ("DiffMa-S/2", "fp32"), ("DiffMa-S/4", "bf16"), ("DiffMa-S/7", "fp32")])
+def test_step_head_kernel_equals_torch_head(dev, tag, dtype):
+    """dm_step_head (patch embedding + pos_embed + conditioning vector + SiLU in one launch) vs the torch head of the fused
+    forward: PatchEmbed conv as unfold + matmul, timestep-table row + y / pooled y2, cat, SiLU (reference model.py:264-281)."""
+    from diffma_b200 import model as M, ops, synth
+    torch.manual_seed(0)
+    net = M.DiffMa_models[tag](input_size=28, dt_rank=16, d_state=16, use_mamba2=False).eval()
+    synth.fill_trained_like_(net, seed=11)
+    net = net.to(dev)
+    p = net.patch_size
+    B = 5
+    b = synth.synthetic_batch(B, tokens=(28 // p) ** 2, seed=21, device=dev)
+    act = torch.float32 if dtype == "fp32" else torch.bfloat16
+    t = torch.tensor([0, 999, 3, 500, 77], device=dev)
+    y2m = b["y2"].mean(1)
+    h_ref = net._embed_patches(b["x"])
+    te = net._t_embedding(t)
+    c = torch.cat((te + b["y"], te + y2m), dim=1)
+    sc_ref = torch.nn.functional.silu(c.float()).to(act)
+    wb = net._patch_tables()
+    h, sc = ops.step_head(b["x"], wb[0], wb[1], p, t, net._t_table(), b["y"], y2m.contiguous(), act)
+    torch.testing.assert_close(h, h_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(sc.float(), sc_ref.float(), **(dict(rtol=1e-5, atol=1e-6) if dtype == "fp32" else dict(rtol=8e-3, atol=1e-3)))
+    # a timestep outside the table poisons its row instead of reading past the table
+    t_bad = t.clone()
+    t_bad[2] = 1000
+    _, sc_bad = ops.step_head(b["x"], wb[0], wb[1], p, t_bad, net._t_table(), b["y"], y2m.contiguous(), act)
+    assert torch.isnan(sc_bad[2].float()).all() and torch.isfinite(sc_bad[[0, 1, 3, 4]].float()).all()
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("with_pre", [False, True])
 def test_folded_attention_layernorm_equals_post_ln_plus_linear(dev, dtype, with_pre):
