@@ -514,12 +514,14 @@ __global__ void __launch_bounds__(kP2Threads, 1) m1_conv_xproj_persistent(const 
 //   One warp per (32 scanned tokens, 64 channels): A = dt_low hi + lo halves read straight from the x_dbl rows (the
 //   m16n8k16 A fragment is 4 words of a row), B = the W_dt rows of the warp's channels, both from L2 / L1.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kDTok = 64;          // scanned tokens per warp: the W_dt fragments (32 registers) are loaded once per 64 x 64 tile
+// (kDTok, the template parameter of m1_delta_kernel: scanned tokens per warp, 64 or 128; the W_dt fragments (32 registers) are
+//  loaded once per kDTok x 64 tile)
 struct DeltaSmem {                 // per warp; every row stride is an odd multiple of 16 B (ldmatrix / 16-byte accesses conflict free)
     __nv_bfloat16 wd[64][kR + 8];  // the warp's W_dt rows
     __nv_bfloat16 at[16][64 + 8];  // dt_low of 16 tokens: [hi 32 | lo 32]
     __half stage[16][64 + 8];      // softplus'ed tile in fragment order -> row-order copy-out
 };
+template <int kDTok>
 __global__ void __launch_bounds__(128) m1_delta_kernel(const __grid_constant__ M1P p, int rows_per_group) {
     using T = __nv_bfloat16;
     __shared__ __align__(16) DeltaSmem smem[4];
@@ -1186,9 +1188,17 @@ int launch_m1(const M1P& p_in, int phases, cudaStream_t stream, size_t sched_byt
         DM_CUDA_TRY(cudaGetLastError());
         if constexpr (sizeof(T) == 2) {
             if (p.g[0].delta != nullptr) {                       // (all groups or none: normalised above)
+                // 128 tokens per warp halve the per-warp prologue (W_dt staging, fragments, bias) -- taken when that still
+                // leaves >= 4 CTAs per SM (headline shape: 592 CTAs = exactly one resident wave on 148 SMs; 50.2 -> 48.1 us for
+                // conv + x_proj + delta), otherwise 64-token warps keep the SMs occupied (batch 8)
                 const int rows = p.B * p.K * p.L;
-                const int grid = p.n_groups * ((rows + kDTok - 1) / kDTok) * (p.D / 256);
-                DM_CUDA_TRY(launch_pdl(kPdlDelta, m1_delta_kernel, dim3(grid), dim3(128), 0, stream, p, rows));
+                const int grid128 = p.n_groups * ((rows + 127) / 128) * (p.D / 256);
+                if (grid128 >= 4 * n_sm) {
+                    DM_CUDA_TRY(launch_pdl(kPdlDelta, m1_delta_kernel<128>, dim3(grid128), dim3(128), 0, stream, p, rows));
+                } else {
+                    const int grid = p.n_groups * ((rows + 63) / 64) * (p.D / 256);
+                    DM_CUDA_TRY(launch_pdl(kPdlDelta, m1_delta_kernel<64>, dim3(grid), dim3(128), 0, stream, p, rows));
+                }
                 DM_CUDA_TRY(cudaGetLastError());
             }
         }
