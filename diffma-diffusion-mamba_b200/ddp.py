@@ -209,6 +209,26 @@ class FlatTrainState:
         by_id = {id(p): o for p, o in zip(self.params, self.offsets)}
         return {n: self.flat_p[by_id[id(p)]:by_id[id(p)] + p.numel()].view_as(p) for n, p in named_params if id(p) in by_id}
 
+    @torch.no_grad()
+    def load_master_state(self, named_params, state_dict: dict, strict: bool = True) -> None:
+        """Load fp32 weights (a checkpoint's ``model`` entry) into an EXISTING state: into the flat masters, then refresh the
+        bf16 shadows.  ``net.load_state_dict`` after construction would write the ``lowp`` leaves' bf16 shadows only and
+        leave their masters stale -- either build the state after loading, or load through this method."""
+        by_id = {id(p): o for p, o in zip(self.params, self.offsets)}
+        missing = []
+        for n, p in named_params:
+            if id(p) not in by_id:
+                continue
+            if n not in state_dict:
+                missing.append(n)
+                continue
+            o = by_id[id(p)]
+            self.flat_p[o:o + p.numel()].view_as(p).copy_(state_dict[n].to(self.flat_p.device, torch.float32))
+        if missing and strict:
+            raise KeyError(f"load_master_state: missing {len(missing)} entries, e.g. {missing[:3]}")
+        if self.flat_s is not None:
+            self.flat_s.copy_(self.flat_p)
+
     def ema_state(self, named_params) -> dict:
         """name -> EMA tensor (views into the flat EMA buffer), for checkpoints (train.py:293-300 saves ema.state_dict())."""
         if self.ema is None:

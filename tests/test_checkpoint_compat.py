@@ -141,3 +141,9 @@ def test_bf16_leaf_state_saves_fp32_masters(tmp_path):
     fresh = M.DiffMa_models["DiffMa-S/7"](input_size=28, dt_rank=16, d_state=16, use_mamba2=False)
     checkpoint.load_checkpoint(path, fresh, kind="model")
     torch.testing.assert_close(fresh.state_dict()[k], ref[k], rtol=0, atol=0)
+    # resuming INTO an existing bf16-leaf state goes through the masters (net.load_state_dict would only touch the shadows)
+    newer = {n: v + 0.25 for n, v in ck["model"].items() if v.dtype == torch.float32}
+    st.load_master_state(net.named_parameters(), newer)
+    torch.testing.assert_close(st.master_state(net.named_parameters())[k], ref[k] + 0.25, rtol=0, atol=0)
+    torch.testing.assert_close(p.detach().float(), (ref[k] + 0.25).to(torch.bfloat16).float(), rtol=0, atol=0)
+    st.check_views()
