@@ -90,9 +90,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 }  // namespace p3
 
+// kSplit (small batches: fewer tiles than half the SMs): a tile is shared by the two CTAs of a cluster, CTA `half` convolves
+// channel slices half * 8 .. half * 8 + 7 and contracts them against its half of W_x (split K); CTA 1 then hands its
+// partial accumulator (128 x 64 fp32) to CTA 0 through distributed shared memory, CTA 0 adds it to its own and writes the
+// x_dbl rows.  One tile per cluster (grid = 2 x tiles), so nothing persists across tiles.
+template <bool kSplit>
 __global__ void __launch_bounds__(p3::kThreads, 1)
 m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_per_group) {
     using namespace p3;
+    constexpr int kNSl = kSplit ? kNS / 2 : kNS;                             // slices this CTA works through
+    const int half = kSplit ? static_cast<int>(blockIdx.x & 1) : 0;
+    const int s0 = half * kNSl;                                              // first (global) slice of this CTA
     using T = __nv_bfloat16;
     constexpr int kD = 1024;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -126,7 +134,8 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
     uint32_t tiles_done = 0u;               // parity bookkeeping: A buffer ab has been handed to the MMA 8 * tiles_done + (s >> 1) times
     const int pr = tid & 31, seg = tid >> 5;          // conv role: channel pair of the slice, 8-token segment
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tiles_done) {
+    for (int tile = kSplit ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x); tile < n_tiles;
+         tile += kSplit ? n_tiles : static_cast<int>(gridDim.x), ++tiles_done) {
         const int g = tile / tiles_per_group, t_in = tile - g * tiles_per_group;
         const M1G& G = p.g[g];
         const int row0 = t_in * kTile;                                       // first row of the tile inside the group
@@ -169,8 +178,9 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
         // W_x chunk of this thread: row n = tid / 8, chunk cc = tid % 8 of every 64-channel slice (128-byte swizzle)
         const T* w_src = static_cast<const T*>(G.wx) + static_cast<int64_t>(tid >> 3) * kD + (tid & 7) * 8;
         const uint32_t w_dst = base + (tid >> 3) * 128 + ((((tid & 7) ^ ((tid >> 3) & 7))) << 4);
-        auto stage = [&](int s) {                                            // x rows (+ W_x) of slice s -> XS[s % 3] (WX[s])
-            const uint32_t dst0 = base + kOffXS + (s % 3) * kXSBytes;
+        auto stage = [&](int ls) {                                           // x rows (+ W_x) of local slice ls -> XS[ls % 3] (WX[s])
+            const int s = s0 + ls;
+            const uint32_t dst0 = base + kOffXS + (ls % 3) * kXSBytes;
 #pragma unroll
             for (int q = 0; q < 3; ++q)
                 if (cp_src[q] != nullptr) cp_async16(dst0 + cp_dst[q], cp_src[q] + s * kSl);
@@ -203,24 +213,25 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
         }
         // conv weights of this thread's two channels of a slice; fetched one slice ahead (an L2 round trip per slice on the
         // critical path otherwise)
-        float4 w0n = __ldg(reinterpret_cast<const float4*>(conv_w + static_cast<int64_t>(2 * pr) * kW));
-        float4 w1n = __ldg(reinterpret_cast<const float4*>(conv_w + static_cast<int64_t>(2 * pr + 1) * kW));
-        float2 bbn = conv_b ? __ldg(reinterpret_cast<const float2*>(conv_b + 2 * pr)) : make_float2(0.f, 0.f);
+        float4 w0n = __ldg(reinterpret_cast<const float4*>(conv_w + static_cast<int64_t>(s0 * kSl + 2 * pr) * kW));
+        float4 w1n = __ldg(reinterpret_cast<const float4*>(conv_w + static_cast<int64_t>(s0 * kSl + 2 * pr + 1) * kW));
+        float2 bbn = conv_b ? __ldg(reinterpret_cast<const float2*>(conv_b + s0 * kSl + 2 * pr)) : make_float2(0.f, 0.f);
 
-        for (int s = 0; s < kNS; ++s) {
-            if (s + 2 < kNS) stage(s + 2); else cp_async_commit();           // (empty group keeps the wait counts uniform)
+        for (int ls = 0; ls < kNSl; ++ls) {
+            const int s = s0 + ls;                                           // global slice: channels s * 64 .. s * 64 + 63
+            if (ls + 2 < kNSl) stage(ls + 2); else cp_async_commit();        // (empty group keeps the wait counts uniform)
             const float4 w0 = w0n, w1 = w1n;
             const float2 bb = bbn;
-            if (s + 1 < kNS) {
+            if (ls + 1 < kNSl) {
                 const int c = (s + 1) * kSl + 2 * pr;
                 w0n = __ldg(reinterpret_cast<const float4*>(conv_w + static_cast<int64_t>(c) * kW));
                 w1n = __ldg(reinterpret_cast<const float4*>(conv_w + static_cast<int64_t>(c + 1) * kW));
                 if (conv_b) bbn = __ldg(reinterpret_cast<const float2*>(conv_b + c));
             }
             cp_async_wait<2>();                                              // slice s has landed (this thread's copies)
-            if (s == 0) __syncthreads();                                     // ... and everybody else's (later slices: the loop barrier)
-            const int ab = s & 1;
-            const uint8_t* xs = sm + kOffXS + (s % 3) * kXSBytes + pr * 4 + r_first * 128;
+            if (ls == 0) __syncthreads();                                    // ... and everybody else's (later slices: the loop barrier)
+            const int ab = ls & 1;
+            const uint8_t* xs = sm + kOffXS + (ls % 3) * kXSBytes + pr * 4 + r_first * 128;
             uint8_t* as = sm + kOffAS + ab * kASBytes;
             T* u_s = u_out + s * kSl;
             // branch-free path: 11 independent window loads, the thread's two channels on packed fp32x2 math
@@ -233,7 +244,7 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
             const uint64_t k0 = pack2(w0.x, w1.x), k1 = pack2(w0.y, w1.y), k2 = pack2(w0.z, w1.z), k3 = pack2(w0.w, w1.w);
             const uint64_t kb = pack2(bb.x, bb.y), half2 = pack2(0.5f, 0.5f);
             // the MMA that read AS[s % 2] two slices ago must have completed
-            const uint32_t used = tiles_done * (kNS / 2) + (s >> 1);
+            const uint32_t used = tiles_done * (kNSl / 2) + (ls >> 1);
             if (used > 0) wait_bounded(bar0 + 8 * ab, (used - 1) & 1);
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
@@ -282,13 +293,40 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
                 const uint64_t ad = desc_sw128(base + kOffAS + ab * kASBytes);
                 const uint64_t bd = desc_sw128(base + s * (kE * 128));
 #pragma unroll
-                for (int k = 0; k < kSl / 16; ++k) umma(tmem_acc, ad + 2 * k, bd + 2 * k, (s | k) != 0);
+                for (int k = 0; k < kSl / 16; ++k) umma(tmem_acc, ad + 2 * k, bd + 2 * k, (ls | k) != 0);
                 commit(bar0 + 8 * ab);
-                if (s == kNS - 1) commit(bar0 + 16);
+                if (ls == kNSl - 1) commit(bar0 + 16);
             }
         }
-        // ---- epilogue (warps 0..3): accumulator (128 rows x 64) -> x_dbl rows ----
-        if (warp < 4) {
+        // ---- split K: CTA 1's partial accumulator -> CTA 0's shared memory (the upper half of its W_x region, which only
+        //      holds slices 8..15 and is never touched by CTA 0), 272-byte rows ----
+        constexpr int kPartStride = 68;                                      // floats per partial row (16-byte accesses conflict free)
+        float* part = reinterpret_cast<float*>(sm + kWXBytes / 2);
+        if constexpr (kSplit) {
+            if (half == 1 && warp < 4) {
+                wait_bounded(bar0 + 16, tiles_done & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int r = warp * 32 + lane;
+                uint32_t remote;                                             // the same offset in CTA 0's shared window
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(part + r * kPartStride)), "r"(0));
+                uint32_t v[32];
+#pragma unroll
+                for (int hsel = 0; hsel < 2; ++hsel) {
+                    tmem_ld32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16) + 32 * hsel, v);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (32 * hsel + i) * 4),
+                                     "r"(v[i]), "r"(v[i + 1]), "r"(v[i + 2]), "r"(v[i + 3]) : "memory");
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            // every thread of both CTAs: CTA 1's stores are complete and visible before CTA 0 reads them; CTA 0's shared
+            // memory stays allocated until CTA 1 has arrived
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+        // ---- epilogue (warps 0..3 [of CTA 0]): accumulator (128 rows x 64) -> x_dbl rows ----
+        if (warp < 4 && half == 0) {
             wait_bounded(bar0 + 16, tiles_done & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int r = warp * 32 + lane;
@@ -296,6 +334,16 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
             float* rowp = G.x_dbl + static_cast<int64_t>(row0 + (ok ? r : 0)) * kE;
             uint32_t v[32];
             tmem_ld32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16), v);             // columns 0..31: dt_low
+            if constexpr (kSplit) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(part + r * kPartStride + i);
+                    v[i] = __float_as_uint(__uint_as_float(v[i]) + q.x);
+                    v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + q.y);
+                    v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + q.z);
+                    v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + q.w);
+                }
+            }
             if (ok) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
@@ -308,6 +356,16 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
                 }
             }
             tmem_ld32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16) + 32, v);        // columns 32..63: B, C
+            if constexpr (kSplit) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(part + r * kPartStride + 32 + i);
+                    v[i] = __float_as_uint(__uint_as_float(v[i]) + q.x);
+                    v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + q.y);
+                    v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + q.z);
+                    v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + q.w);
+                }
+            }
             if (ok) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)

@@ -1158,13 +1158,35 @@ int launch_m1(const M1P& p_in, int phases, cudaStream_t stream, size_t sched_byt
             if constexpr (sizeof(T) == 2) {
                 static PerDeviceOnce tcfg;
                 if (!tcfg.done(dev)) {
-                    DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, p3::kSmemBytes));
+                    DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p3::kSmemBytes));
+                    DM_CUDA_TRY(cudaFuncSetAttribute(m1_conv_xproj_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p3::kSmemBytes));
                     tcfg.set(dev);
                 }
                 const int rows = p.B * p.K * p.L;
                 const int tiles_per_group = (rows + p3::kTile - 1) / p3::kTile;
                 const int n_tiles = tiles_per_group * p.n_groups;
-                DM_CUDA_TRY(launch_pdl(kPdlConvX, m1_conv_xproj_tc, dim3(n_tiles < n_sm ? n_tiles : n_sm), dim3(p3::kThreads), p3::kSmemBytes, stream, p, rows, tiles_per_group));
+                static const int split_k = env_int("DM_CONVX_SPLIT", 1);
+                if (split_k && 2 * n_tiles <= n_sm) {
+                    // small batches: two CTAs (a cluster) per tile, the channel slices split between them (batch 8: 74 tiles
+                    // would leave half of the 148 SMs idle)
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(2 * n_tiles);
+                    cfg.blockDim = dim3(p3::kThreads);
+                    cfg.dynamicSmemBytes = p3::kSmemBytes;
+                    cfg.stream = stream;
+                    cudaLaunchAttribute attr[2];
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = 2;
+                    attr[0].val.clusterDim.y = 1;
+                    attr[0].val.clusterDim.z = 1;
+                    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    attr[1].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = attr;
+                    cfg.numAttrs = (pdl_mask() & kPdlConvX) ? 2 : 1;
+                    DM_CUDA_TRY(cudaLaunchKernelEx(&cfg, m1_conv_xproj_tc<true>, p, rows, tiles_per_group));
+                } else {
+                    DM_CUDA_TRY(launch_pdl(kPdlConvX, m1_conv_xproj_tc<false>, dim3(n_tiles < n_sm ? n_tiles : n_sm), dim3(p3::kThreads), p3::kSmemBytes, stream, p, rows, tiles_per_group));
+                }
             }
         } else if (!split && p.D == 1024 && bytes2 <= 227 * 1024) {                 // persistent mma.sync kernel, W_x resident in shared memory
             static PerDeviceOnce cfg;
