@@ -502,13 +502,20 @@ step_head_kernel(const float* __restrict__ x, const float* __restrict__ wp, cons
 #pragma unroll
     for (int k = 0; k < kHeadTok; ++k) acc[k][0] = acc[k][1] = 0.f;
     const float2* w2 = reinterpret_cast<const float2*>(wp) + tid;        // columns 2 tid, 2 tid + 1 of row j
-    for (int j = 0; j < J; ++j) {
-        const float2 w = __ldg(w2 + static_cast<int64_t>(j) * (D / 2));
+    for (int j0 = 0; j0 < J; j0 += 8) {                                  // 8 weight rows in flight (a load per row was a serial
+        float2 w[8];                                                     // chain of L2 round trips: 15 us for this kernel)
 #pragma unroll
-        for (int k = 0; k < kHeadTok; ++k) {
-            const float v = px[k * J + j];
-            acc[k][0] = fmaf(v, w.x, acc[k][0]);
-            acc[k][1] = fmaf(v, w.y, acc[k][1]);
+        for (int i = 0; i < 8; ++i)
+            w[i] = (j0 + i < J) ? __ldg(w2 + static_cast<int64_t>(j0 + i) * (D / 2)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = min(j0 + i, J - 1);                            // (rows past J carry zero weights)
+#pragma unroll
+            for (int k = 0; k < kHeadTok; ++k) {
+                const float v = px[k * J + j];
+                acc[k][0] = fmaf(v, w[i].x, acc[k][0]);
+                acc[k][1] = fmaf(v, w[i].y, acc[k][1]);
+            }
         }
     }
 #pragma unroll
