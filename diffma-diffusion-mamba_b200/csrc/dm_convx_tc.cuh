@@ -128,6 +128,11 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_acc = *tmem_slot;
     pdl_launch_dependents();
+    if constexpr (kSplit) {
+        // distributed shared memory may only be touched once its CTA is known to be running: both CTAs arrive here, the
+        // matching wait sits in front of the exchange (by then long complete)
+        asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    }
 
     const int n_tiles = p.n_groups * tiles_per_group;
     int cur_group = -1;
@@ -303,6 +308,7 @@ m1_conv_xproj_tc(const __grid_constant__ M1P p, int rows_per_group, int tiles_pe
         constexpr int kPartStride = 68;                                      // floats per partial row (16-byte accesses conflict free)
         float* part = reinterpret_cast<float*>(sm + kWXBytes / 2);
         if constexpr (kSplit) {
+            asm volatile("barrier.cluster.wait.aligned;" ::: "memory");     // (start-of-kernel arrival of the peer CTA)
             if (half == 1 && warp < 4) {
                 wait_bounded(bar0 + 16, tiles_done & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
