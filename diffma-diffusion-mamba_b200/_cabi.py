@@ -17,7 +17,7 @@ DM_OUT_SCAN_ORDER, DM_OUT_TOKEN_ORDER = 0, 1
 
 EXPORTS = ("dm_mamba1_scan_fwd", "dm_mamba1_scan_phase", "dm_mamba1_sched_workspace_bytes", "dm_mamba1_scan_bwd", "dm_mamba1_bwd_chunk_tokens", "dm_mamba2_ssd_fwd", "dm_mamba2_ssd_bwd", "dm_merge_directions_multi", "dm_spiral_pre", "dm_spiral_post_ln",
            "dm_spiral_post_mix", "dm_spiral_post_mix_pre", "dm_spiral_pre_bwd", "dm_spiral_post_mix_bwd", "dm_spiral_post_ln_bwd",
-           "dm_merge_directions", "dm_gemm_bf16_tn", "dm_gemm_bf16_tn_ex", "dm_p_sample_update", "dm_adamw_ema_step", "dm_adamw_ema_step_ex", "dm_spiral_post_mix_fold", "dm_step_head", "dm_version", "dm_status_string", "dm_last_cuda_error",
+           "dm_merge_directions", "dm_gemm_bf16_tn", "dm_gemm_bf16_tn_ex", "dm_p_sample_update", "dm_adamw_ema_step", "dm_adamw_ema_step_ex", "dm_spiral_post_mix_fold", "dm_step_head", "dm_final_linear_unpatchify", "dm_version", "dm_status_string", "dm_last_cuda_error",
            "dm_build_info")
 
 
@@ -177,6 +177,8 @@ def lib() -> C.CDLL:
     L.dm_adamw_ema_step.restype = C.c_int
     f64 = C.c_double
     L.dm_adamw_ema_step.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, f64, f64, vp]
+    L.dm_final_linear_unpatchify.restype = C.c_int
+    L.dm_final_linear_unpatchify.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.dm_step_head.restype = C.c_int
     L.dm_step_head.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, i32, i32, vp]
     L.dm_spiral_post_mix_fold.restype = C.c_int

@@ -560,6 +560,97 @@ extern "C" int dm_step_head(const float* x, const float* patch_weight, const flo
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Tail of DiffMa.forward (reference model.py:295-301, FinalLayer.linear + unpatchify): out = hn . W^T + b, written straight
+// into the (B, C_out, S, S) image layout  [token (gy, gx), feature n = (py * p + px) * C_out + c  ->  out[b][c][gy p + py][gx p + px]].
+// bf16 only: a 64-token x N x 512 tensor-core tile per CTA (4 warps x m16, mma.sync; the GEMM is 0.1 GFLOP -- the point is
+// to drop the separate GEMM launch and the permute copy behind it).  N = p * p * C_out <= 128.
+// ------------------------------------------------------------------------------------------------------
+namespace dm {
+namespace {
+constexpr int kTailTok = 64, kTailK = 512, kTailLd = kTailK + 8;         // +8 bf16: ldmatrix rows land in different banks
+__global__ void __launch_bounds__(128)
+final_linear_unpatchify_kernel(const __nv_bfloat16* __restrict__ hn, const __nv_bfloat16* __restrict__ w,
+                               const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int rows, int L, int g,
+                               int patch, int c_out, int N) {
+    extern __shared__ __align__(16) uint8_t tail_smem[];
+    __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(tail_smem);                        // [64][520]
+    __nv_bfloat16* Ws = As + kTailTok * kTailLd;                                            // [N][520]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = blockIdx.x * kTailTok;
+    for (int i = tid; i < N * (kTailK / 8); i += 128) {                                     // weights: independent of the predecessor
+        const int n = i / (kTailK / 8), c = i % (kTailK / 8);
+        cp_async16(smem_u32(Ws + n * kTailLd + c * 8), w + static_cast<int64_t>(n) * kTailK + c * 8);
+    }
+    pdl_wait();
+    for (int i = tid; i < kTailTok * (kTailK / 8); i += 128) {
+        const int r = i / (kTailK / 8), c = i % (kTailK / 8);
+        const int row = min(row0 + r, rows - 1);
+        cp_async16(smem_u32(As + r * kTailLd + c * 8), hn + static_cast<int64_t>(row) * kTailK + c * 8);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int S = g * patch;
+    for (int nb = 0; nb < N; nb += 32) {                                                    // 4 n-tiles of 8 per pass
+        float acc[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+        for (int k0 = 0; k0 < kTailK; k0 += 16) {
+            uint32_t a[4];
+            ldmatrix_x4(a[0], a[1], a[2], a[3], smem_u32(As + (warp * 16 + (lane & 15)) * kTailLd + k0 + (lane >> 4) * 8));
+#pragma unroll
+            for (int tp = 0; tp < 2; ++tp) {                                                // two n-tiles per ldmatrix.x4
+                uint32_t b[4];
+                const int n = nb + tp * 16 + (lane & 7) + ((lane >> 4) << 3);
+                ldmatrix_x4(b[0], b[1], b[2], b[3], smem_u32(Ws + min(n, N - 1) * kTailLd + k0 + ((lane >> 3) & 1) * 8));
+                mma_bf16_16816(acc[2 * tp], a, b[0], b[1]);
+                mma_bf16_16816(acc[2 * tp + 1], a, b[2], b[3]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = row0 + warp * 16 + (lane >> 2) + (e >> 1) * 8;
+                const int n = nb + t * 8 + 2 * (lane & 3) + (e & 1);
+                if (r < rows && n < N) {
+                    const int b = r / L, l = r - b * L, gy = l / g, gx = l - gy * g;
+                    const int c = n % c_out, pq = n / c_out, py = pq / patch, px = pq - py * patch;
+                    const float v = acc[t][e] + __bfloat162float(bias[n]);
+                    out[((static_cast<int64_t>(b) * c_out + c) * S + gy * patch + py) * S + gx * patch + px] = __float2bfloat16_rn(v);
+                }
+            }
+    }
+}
+}  // namespace
+}  // namespace dm
+
+extern "C" int dm_final_linear_unpatchify(const void* hn, const void* weight, const void* bias, void* out, int32_t batch,
+                                          int32_t grid_side, int32_t patch, int32_t out_channels, int32_t d_model,
+                                          int32_t act_dtype, void* stream) {
+    if (!hn || !weight || !bias || !out || batch <= 0 || grid_side <= 0 || patch <= 0 || out_channels <= 0) return DM_ERR_INVALID_ARG;
+    const int N = patch * patch * out_channels;
+    if (d_model != dm::kTailK || act_dtype != DM_BF16 || N > 128) return DM_ERR_UNSUPPORTED;
+    if (!dm::aligned16(hn) || !dm::aligned16(weight)) return DM_ERR_INVALID_ARG;
+    const int L = grid_side * grid_side, rows = batch * L;
+    const size_t smem = static_cast<size_t>(dm::kTailTok + N) * dm::kTailLd * sizeof(__nv_bfloat16);
+    int dev = 0, n_sm = 0;
+    if (int e = dm::current_device(&dev, &n_sm); e != DM_OK) return e;
+    static dm::PerDeviceOnce cfg;
+    if (!cfg.done(dev)) {
+        DM_CUDA_TRY(cudaFuncSetAttribute(dm::final_linear_unpatchify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>((dm::kTailTok + 128) * dm::kTailLd * sizeof(__nv_bfloat16))));
+        cfg.set(dev);
+    }
+    DM_CUDA_TRY(dm::launch_pdl(dm::kPdlRow, dm::final_linear_unpatchify_kernel, dim3((rows + dm::kTailTok - 1) / dm::kTailTok),
+                               dim3(128), smem, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(hn),
+                               static_cast<const __nv_bfloat16*>(weight), static_cast<const __nv_bfloat16*>(bias),
+                               static_cast<__nv_bfloat16*>(out), rows, L, grid_side, patch, out_channels, N));
+    DM_CUDA_TRY(cudaGetLastError());
+    return DM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // One reverse-diffusion update (reference gaussian_diffusion.py: p_mean_variance :254-332 with LEARNED_RANGE variance
 // and epsilon prediction, p_sample :376-417) as ONE elementwise kernel instead of ~35 tiny launches + 9 table gathers:
 //   eps, v = split(model_out);  logvar = frac*log(beta_t) + (1-frac)*posterior_logvar_t,  frac = (v+1)/2

@@ -285,6 +285,10 @@ class DiffMa(nn.Module):
                 lw, lb = self._cached(f"fl_lin_{act}", [self.final_layer.linear.weight, self.final_layer.linear.bias],
                                       lambda: (self.final_layer.linear.weight.to(act).contiguous(),
                                                self.final_layer.linear.bias.to(act).contiguous()))
+                if _STEP_HEAD:      # FinalLayer.linear + unpatchify in one launch (bf16, patch^2 * out_channels <= 128)
+                    img = ops.final_linear_unpatchify(x2[0], lw, lb, B, self.patch_size, self.out_channels)
+                    if img is not None:
+                        return img
                 o = torch.nn.functional.linear(hn, lw, lb)
             return self.unpatchify(o)
         x = self.x_embedder(x) + self.pos_embed

@@ -655,6 +655,26 @@ def step_head(x, patch_weight, pos_bias, patch: int, t, t_table, y, y2_mean, act
     return h, sc
 
 
+def final_linear_unpatchify(hn, weight, bias, batch: int, patch: int, out_channels: int):
+    """Tail of DiffMa.forward in one launch (``dm_final_linear_unpatchify``): hn (B*L, 512) bf16 -> (B, C_out, S, S) bf16.
+    Returns None when the shape is outside the kernel's range (the caller then runs the GEMM and the permute)."""
+    N = patch * patch * out_channels
+    rows, D = hn.shape
+    if (hn.dtype != torch.bfloat16 or D != 512 or N > 128 or not hn.is_contiguous() or weight.dtype != torch.bfloat16
+            or not weight.is_contiguous() or bias.dtype != torch.bfloat16 or tuple(weight.shape) != (N, D) or rows % batch):
+        return None
+    L = rows // batch
+    g = int(round(L ** 0.5))
+    if g * g != L:
+        return None
+    out = torch.empty((batch, out_channels, g * patch, g * patch), dtype=torch.bfloat16, device=hn.device)
+    st = _cabi.lib().dm_final_linear_unpatchify(hn.data_ptr(), weight.data_ptr(), bias.contiguous().data_ptr(), out.data_ptr(),
+                                                batch, g, patch, out_channels, D, _cabi.DM_BF16, _stream_handle(hn.device))
+    _cabi.check(st, "dm_final_linear_unpatchify")
+    LAUNCH_COUNTER["kernels"] += 1
+    return out
+
+
 def _mod2d(mod: torch.Tensor) -> torch.Tensor:
     """adaLN output (B, 3D) fp32, rows may be strided (a slice of the all-blocks GEMM), channels contiguous."""
     if mod.dtype != torch.float32 or mod.dim() != 2 or mod.stride(1) != 1 or not mod.is_cuda or mod.stride(0) % 4:

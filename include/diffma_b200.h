@@ -279,6 +279,14 @@ int dm_step_head(const float* x, const float* patch_weight, const float* pos_bia
                  int32_t image_size, int32_t patch, const int64_t* t, const float* t_table, int32_t table_rows, const float* y,
                  const float* y2_mean, void* silu_c, int32_t d_model, int32_t act_dtype, void* stream);
 
+/* Tail of DiffMa.forward (reference model.py:295-301): FinalLayer.linear on the modulated rows hn (B*L, D) and unpatchify in one
+ * launch: out (B, out_channels, S, S), S = grid_side * patch, out[b][c][gy p + py][gx p + px] = (hn . W^T + bias)[(py p + px) *
+ * out_channels + c] of token (gy, gx).  bf16 only, D = 512, patch * patch * out_channels <= 128 (else DM_ERR_UNSUPPORTED:
+ * the caller runs the GEMM and the permute). */
+int dm_final_linear_unpatchify(const void* hn, const void* weight, const void* bias, void* out, int32_t batch,
+                               int32_t grid_side, int32_t patch, int32_t out_channels, int32_t d_model, int32_t act_dtype,
+                               void* stream);
+
 /* Adjoints of the three row kernels above for the training step (autograd of block/mamba_block.py:100-115, reached from
  * train.py:259).  Per-batch-element and per-parameter gradients are ACCUMULATED (atomics) into buffers the caller zeroed:
  *   dm_spiral_pre_bwd       d_out2 (2, rows, d) act dtype -> dx (rows, d) fp32 [= d skip]; d_mod[:, 0:d] += d shift,

@@ -220,6 +220,30 @@ def test_step_head_kernel_equals_torch_head(dev, tag, dtype):
     assert torch.isnan(sc_bad[2].float()).all() and torch.isfinite(sc_bad[[0, 1, 3, 4]].float()).all()
 
 
+@pytest.mark.parametrize("tag,B", [("DiffMa-S/2", 3), ("DiffMa-S/4", 5)])
+def test_final_linear_unpatchify_kernel_equals_linear_plus_unpatchify(dev, tag, B):
+    """dm_final_linear_unpatchify vs FinalLayer.linear (bf16 GEMM) + DiffMa.unpatchify (reference model.py:295-301, 246-262):
+    N = 32 (patch 2) and N = 128 (patch 4), row counts that are not multiples of the 64-token tile."""
+    from diffma_b200 import model as M, ops, synth
+    torch.manual_seed(0)
+    net = M.DiffMa_models[tag](input_size=28, dt_rank=16, d_state=16, use_mamba2=False).eval()
+    synth.fill_trained_like_(net, seed=11)
+    net = net.to(dev)
+    p, L = net.patch_size, (28 // net.patch_size) ** 2
+    g = torch.Generator().manual_seed(5)
+    hn = torch.randn(B * L, 512, generator=g).to(dev).to(torch.bfloat16)
+    lw = net.final_layer.linear.weight.detach().to(torch.bfloat16).contiguous()
+    lb = net.final_layer.linear.bias.detach().to(torch.bfloat16).contiguous()
+    got = ops.final_linear_unpatchify(hn, lw, lb, B, p, net.out_channels)
+    assert got is not None and got.dtype == torch.bfloat16 and tuple(got.shape) == (B, net.out_channels, 28, 28)
+    want = net.unpatchify(torch.nn.functional.linear(hn, lw, lb).view(B, L, -1))
+    # both accumulate in fp32 and round once to bf16; the summation orders differ
+    torch.testing.assert_close(got.float(), want.float(), rtol=1.6e-2, atol=2e-3)
+    exact = net.unpatchify((hn.double() @ lw.double().t() + lb.double()).view(B, L, -1))
+    assert float((got.double() - exact).abs().max()) <= 1.5 * float((want.double() - exact).abs().max()) + 1e-3
+    assert ops.final_linear_unpatchify(hn.float(), lw, lb, B, p, net.out_channels) is None     # fp32 rows: caller's GEMM path
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("with_pre", [False, True])
 def test_folded_attention_layernorm_equals_post_ln_plus_linear(dev, dtype, with_pre):
