@@ -375,6 +375,12 @@ def timed_steps(sampler, steps, world, device, min_seconds=0.5, max_repeats=50):
     return reps[len(reps) // 2], len(reps)
 
 
+# y2 enters the model through its token mean only: dm_step_head takes that mean inside the step's first kernel (same device-resident
+# rate, and the end-to-end path needs no separate reduction after each step's H2D: 9 988 -> 10 065 images/s).  DIFFMA_POOL_Y2=1
+# pools once per batch outside the graph instead (GraphedSampler(pool_y2=True)).
+POOL_Y2 = os.environ.get("DIFFMA_POOL_Y2", "0") != "0"
+
+
 def side_config(args, device, world, model, batch, input_size, mamba2, steps=10):
     """Device-resident images/s of another BASELINE config in the same process (same method as the headline value)."""
     import copy
@@ -392,7 +398,7 @@ def side_config(args, device, world, model, batch, input_size, mamba2, steps=10)
             return net(x, t, **kwargs).float()
 
     sampler = GraphedSampler(diffusion, model_fn, tuple(b["x"].shape), dict(y=b["y"], y2=b["y2"], w=b["w"]), device,
-                             clip_denoised=False, warmup=2, use_graph=not args.no_graph, pool_y2=True)
+                             clip_denoised=False, warmup=2, use_graph=not args.no_graph, pool_y2=POOL_Y2)
     sampler.reset(b["x"])
     for _ in range(3):
         sampler.step()
@@ -441,7 +447,7 @@ def main():
     shape = tuple(dev_in["x"].shape)
     ops.LAUNCH_COUNTER["kernels"] = 0
     sampler = GraphedSampler(diffusion, model_fn, shape, kw, device, clip_denoised=False, warmup=2,
-                             use_graph=not args.no_graph, pool_y2=True)
+                             use_graph=not args.no_graph, pool_y2=POOL_Y2)
     launches_per_step = sampler.kernels_per_step
 
     # ---- device-resident timing --------------------------------------------------------------------

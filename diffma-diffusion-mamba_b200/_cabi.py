@@ -180,7 +180,7 @@ def lib() -> C.CDLL:
     L.dm_final_linear_unpatchify.restype = C.c_int
     L.dm_final_linear_unpatchify.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.dm_step_head.restype = C.c_int
-    L.dm_step_head.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, i32, i32, vp]
+    L.dm_step_head.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, i32, vp]
     L.dm_spiral_post_mix_fold.restype = C.c_int
     L.dm_spiral_post_mix_fold.argtypes = [C.POINTER(SpiralFoldArgs), vp]
     L.dm_adamw_ema_step_ex.restype = C.c_int

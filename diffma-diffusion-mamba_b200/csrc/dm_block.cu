@@ -458,7 +458,8 @@ extern "C" int dm_spiral_post_mix_fold(const dm_spiral_fold_args* a, void* strea
 //   h = PatchEmbed(x) + pos_embed        conv with kernel = stride = patch  ==  (C p p) -> D matvec per token
 //   c = cat(t_emb[t] + y, t_emb[t] + mean_T(y2));  the adaLN Linears all consume silu(c): emitted directly, act dtype
 // CTAs [0, n_tok_ctas): 16 tokens each, 256 threads x 2 output columns, the patch pixels gathered from NCHW into shared
-// memory, W (J, D) streamed through L2 (32 KB for patch 2).  CTAs [n_tok_ctas, n_tok_ctas + B): one batch row of c each.
+// memory, W (J, D) streamed through L2 (32 KB for patch 2).  CTAs [n_tok_ctas, n_tok_ctas + 8 B): one 64-column slab of one
+// batch row of c each (incl. the token mean of an un-pooled y2).
 // Replaces: unfold-copy, fp32 SIMT GEMM, bias/pos add, index_select, two adds, cat, silu, cast  (8 launches).
 // ------------------------------------------------------------------------------------------------------
 namespace dm {
@@ -469,20 +470,39 @@ __global__ void __launch_bounds__(256)
 step_head_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ posb,
                  float* __restrict__ h, int B, int C, int Himg, int patch, const int64_t* __restrict__ t,
                  const float* __restrict__ table, int table_rows, const float* __restrict__ y,
-                 const float* __restrict__ y2m, T* __restrict__ sc, int n_tok_ctas) {
+                 const float* __restrict__ y2m, int y2_tokens, T* __restrict__ sc, int n_tok_ctas) {
     constexpr int D = 512;
     extern __shared__ float px[];                       // [kHeadTok][J]
     const int tid = threadIdx.x;
     const int g = Himg / patch, L = g * g, J = C * patch * patch;
     pdl_wait();
-    if (static_cast<int>(blockIdx.x) >= n_tok_ctas) {   // ---- conditioning row ----
-        const int b = blockIdx.x - n_tok_ctas;
+    if (static_cast<int>(blockIdx.x) >= n_tok_ctas) {   // ---- conditioning vector: CTA = (batch row, slab of 64 columns) ----
+        const int cb = blockIdx.x - n_tok_ctas;
+        const int b = cb >> 3, c0 = (cb & 7) * 64;
         const int64_t tt = t[b];
         const bool ok = tt >= 0 && tt < table_rows;     // (an index beyond the table: poison the row instead of reading past it)
-        for (int d = tid; d < D; d += 256) {
+        // token mean of y2 (reference model.py:276) for un-pooled (B, T, D) input: thread = (row lane rl, 4 columns), every
+        // load of the slab in flight at once, then a shared-memory reduction over the 16 row lanes.  T <= 1: already pooled.
+        const int T2 = y2_tokens <= 1 ? 1 : y2_tokens;
+        const int rl = tid >> 4, c4 = (tid & 15) * 4;
+        const float* src = y2m + static_cast<int64_t>(b) * T2 * D + c0 + c4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = rl; r < T2; r += 16) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(r) * D));
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        float4* red = reinterpret_cast<float4*>(px);   // [16 row lanes][16 column groups]
+        red[tid] = a;
+        __syncthreads();
+        if (tid < 64) {
+            const int g4 = tid >> 2, e = tid & 3;
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sum += reinterpret_cast<const float*>(&red[k * 16 + g4])[e];
+            const int d = c0 + tid;
             const float te = ok ? __ldg(table + tt * D + d) : __int_as_float(0x7fc00000);
             const float c1 = te + __ldg(y + static_cast<int64_t>(b) * D + d);
-            const float c2 = te + __ldg(y2m + static_cast<int64_t>(b) * D + d);
+            const float c2 = te + sum / static_cast<float>(T2);
             sc[static_cast<int64_t>(b) * 2 * D + d] = from_f32<T>(c1 / (1.0f + __expf(-c1)));
             sc[static_cast<int64_t>(b) * 2 * D + D + d] = from_f32<T>(c2 / (1.0f + __expf(-c2)));
         }
@@ -533,27 +553,28 @@ step_head_kernel(const float* __restrict__ x, const float* __restrict__ wp, cons
 
 extern "C" int dm_step_head(const float* x, const float* patch_weight, const float* pos_bias, float* h, int32_t batch,
                             int32_t channels, int32_t image_size, int32_t patch, const int64_t* t, const float* t_table,
-                            int32_t table_rows, const float* y, const float* y2_mean, void* silu_c, int32_t d_model,
-                            int32_t act_dtype, void* stream) {
+                            int32_t table_rows, const float* y, const float* y2_mean, int32_t y2_tokens, void* silu_c,
+                            int32_t d_model, int32_t act_dtype, void* stream) {
     if (!x || !patch_weight || !pos_bias || !h || !t || !t_table || !y || !y2_mean || !silu_c || batch <= 0 || channels <= 0 ||
         image_size <= 0 || patch <= 0 || table_rows <= 0)
         return DM_ERR_INVALID_ARG;
     if (d_model != 512 || image_size % patch) return DM_ERR_UNSUPPORTED;
     if (act_dtype != DM_BF16 && act_dtype != DM_F32) return DM_ERR_UNSUPPORTED;
     const int g = image_size / patch, J = channels * patch * patch;
-    const size_t smem = static_cast<size_t>(dm::kHeadTok) * J * sizeof(float);
+    size_t smem = static_cast<size_t>(dm::kHeadTok) * J * sizeof(float);
     if (smem > 48 * 1024) return DM_ERR_UNSUPPORTED;
+    if (smem < 256 * sizeof(float4)) smem = 256 * sizeof(float4);        // the conditioning CTAs' reduction buffer
     const int n_tok_ctas = (batch * g * g + dm::kHeadTok - 1) / dm::kHeadTok;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (act_dtype == DM_BF16)
-        e = dm::launch_pdl(dm::kPdlRow, dm::step_head_kernel<__nv_bfloat16>, dim3(n_tok_ctas + batch), dim3(256), smem, st, x,
+        e = dm::launch_pdl(dm::kPdlRow, dm::step_head_kernel<__nv_bfloat16>, dim3(n_tok_ctas + 8 * batch), dim3(256), smem, st, x,
                            patch_weight, pos_bias, h, batch, channels, image_size, patch, t, t_table, table_rows, y, y2_mean,
-                           static_cast<__nv_bfloat16*>(silu_c), n_tok_ctas);
+                           y2_tokens, static_cast<__nv_bfloat16*>(silu_c), n_tok_ctas);
     else
-        e = dm::launch_pdl(dm::kPdlRow, dm::step_head_kernel<float>, dim3(n_tok_ctas + batch), dim3(256), smem, st, x,
+        e = dm::launch_pdl(dm::kPdlRow, dm::step_head_kernel<float>, dim3(n_tok_ctas + 8 * batch), dim3(256), smem, st, x,
                            patch_weight, pos_bias, h, batch, channels, image_size, patch, t, t_table, table_rows, y, y2_mean,
-                           static_cast<float*>(silu_c), n_tok_ctas);
+                           y2_tokens, static_cast<float*>(silu_c), n_tok_ctas);
     DM_CUDA_TRY(e);
     DM_CUDA_TRY(cudaGetLastError());
     return DM_OK;

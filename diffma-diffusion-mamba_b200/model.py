@@ -239,17 +239,18 @@ class DiffMa(nn.Module):
         if fused:
             from . import ops
             from .mixer import _act_dtype
-            y2m = y2 if y2.dim() == 2 else torch.mean(y2, dim=1)
             act = _act_dtype(x)
             if (_STEP_HEAD and t.dtype == torch.int64 and x.dtype == torch.float32 and x.is_contiguous()
-                    and y.dtype == torch.float32 and y2m.dtype == torch.float32 and x.shape[2] == x.shape[3]
+                    and y.dtype == torch.float32 and y2.dtype == torch.float32 and x.shape[2] == x.shape[3]
                     and x.shape[1] * self.patch_size ** 2 * 16 * 4 <= 48 * 1024):
+                y2m = y2                               # pooled (N, D) or not (N, T, D): the kernel takes the token mean itself
                 # patch embedding + positional table + conditioning vector (timestep table row + y, + pooled y2) + SiLU in one
                 # launch (dm_step_head) instead of eight
                 wb = self._patch_tables()
                 h, sc = ops.step_head(x, wb[0], wb[1], self.patch_size, t, self._t_table(), y.contiguous(), y2m.contiguous(), act)
                 mods, fmod = self._fused_mods(None, act, silu_c=sc)
             else:
+                y2m = y2 if y2.dim() == 2 else torch.mean(y2, dim=1)
                 h = self._embed_patches(x)
                 te = self._t_embedding(t)
                 c = torch.cat((te + y, te + y2m), dim=1)

@@ -634,21 +634,24 @@ def spiral_post_mix_fold(x, skip, ab, g2, colsum, cvec, ln2_eps, w3, b3, mod, pr
 
 def step_head(x, patch_weight, pos_bias, patch: int, t, t_table, y, y2_mean, act):
     """Head of DiffMa.forward in one launch (``dm_step_head``): returns (h (B, L, D) fp32 = PatchEmbed(x) + pos_embed,
-    silu_c (B, 2D) in ``act`` = silu(cat(t_table[t] + y, t_table[t] + y2_mean)))."""
+    silu_c (B, 2D) in ``act`` = silu(cat(t_table[t] + y, t_table[t] + mean_T(y2)))); ``y2_mean`` may be the pooled (B, D)
+    tensor or the un-pooled (B, T, D) one."""
     _require_cuda(x, "step_head")
     B, Cc, H, Wd = x.shape
     D = pos_bias.shape[-1]
     if H != Wd or H % patch or t.dtype != torch.int64 or tuple(patch_weight.shape) != (Cc * patch * patch, D):
         raise RuntimeError("step_head: square images divisible by the patch, int64 timesteps and a (C*p*p, D) weight expected")
     L = (H // patch) ** 2
-    if tuple(pos_bias.shape) != (L, D) or tuple(y.shape) != (B, D) or tuple(y2_mean.shape) != (B, D):
-        raise RuntimeError("step_head: pos_bias (L, D), y (B, D), y2_mean (B, D) expected")
+    y2_tokens = y2_mean.shape[1] if y2_mean.dim() == 3 else 1             # (B, T, D): the kernel takes the token mean itself
+    if (tuple(pos_bias.shape) != (L, D) or tuple(y.shape) != (B, D) or y2_mean.shape[0] != B or y2_mean.shape[-1] != D
+            or y2_mean.dim() not in (2, 3)):
+        raise RuntimeError("step_head: pos_bias (L, D), y (B, D), y2 (B, D) or (B, T, D) expected")
     h = torch.empty((B, L, D), dtype=torch.float32, device=x.device)
     sc = torch.empty((B, 2 * D), dtype=act, device=x.device)
     st = _cabi.lib().dm_step_head(
         _f32c(x, "x").data_ptr(), _f32c(patch_weight, "patch_weight").data_ptr(), _f32c(pos_bias, "pos_bias").data_ptr(),
         h.data_ptr(), B, Cc, H, patch, t.contiguous().data_ptr(), _f32c(t_table, "t_table").data_ptr(), t_table.shape[0],
-        _f32c(y, "y").data_ptr(), _f32c(y2_mean, "y2_mean").data_ptr(), sc.data_ptr(), D, _dtype_code(sc),
+        _f32c(y, "y").data_ptr(), _f32c(y2_mean, "y2_mean").data_ptr(), y2_tokens, sc.data_ptr(), D, _dtype_code(sc),
         _stream_handle(x.device))
     _cabi.check(st, "dm_step_head")
     LAUNCH_COUNTER["kernels"] += 1

@@ -273,11 +273,13 @@ int dm_spiral_post_mix_fold(const dm_spiral_fold_args* args, void* stream);
  *                             unfolded and transposed), pos_bias (L, D) fp32 = pos_embed + conv bias
  *   silu_c (B, 2D) act dtype = silu(cat(t_table[t] + y, t_table[t] + y2_mean)): what every adaLN Linear consumes; t_table
  *                             (table_rows, D) fp32 = TimestepEmbedder evaluated at the integer steps, t int64 (a step outside
- *                             the table poisons its row with NaN), y / y2_mean (B, D) fp32.
+ *                             the table poisons its row with NaN), y / y2_mean (B, D) fp32 (y2: see y2_tokens).
  * D = 512. */
 int dm_step_head(const float* x, const float* patch_weight, const float* pos_bias, float* h, int32_t batch, int32_t channels,
                  int32_t image_size, int32_t patch, const int64_t* t, const float* t_table, int32_t table_rows, const float* y,
-                 const float* y2_mean, void* silu_c, int32_t d_model, int32_t act_dtype, void* stream);
+                 const float* y2_mean, int32_t y2_tokens, void* silu_c, int32_t d_model, int32_t act_dtype, void* stream);
+/* y2_tokens <= 1: y2_mean is the pooled (B, D) tensor; y2_tokens = T > 1: y2_mean points at the un-pooled (B, T, D) tensor and
+ * the kernel takes the token mean itself (reference model.py:276 `torch.mean(y2, dim=1)`). */
 
 /* Tail of DiffMa.forward (reference model.py:295-301): FinalLayer.linear on the modulated rows hn (B*L, D) and unpatchify in one
  * launch: out (B, out_channels, S, S), S = grid_side * patch, out[b][c][gy p + py][gx p + px] = (hn . W^T + bias)[(py p + px) *

@@ -213,6 +213,9 @@ def test_step_head_kernel_equals_torch_head(dev, tag, dtype):
     h, sc = ops.step_head(b["x"], wb[0], wb[1], p, t, net._t_table(), b["y"], y2m.contiguous(), act)
     torch.testing.assert_close(h, h_ref, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(sc.float(), sc_ref.float(), **(dict(rtol=1e-5, atol=1e-6) if dtype == "fp32" else dict(rtol=8e-3, atol=1e-3)))
+    # un-pooled y2 (B, T, D): the kernel takes the token mean itself (reference model.py:276)
+    _, sc3 = ops.step_head(b["x"], wb[0], wb[1], p, t, net._t_table(), b["y"], b["y2"].contiguous(), act)
+    torch.testing.assert_close(sc3.float(), sc_ref.float(), **(dict(rtol=1e-5, atol=2e-6) if dtype == "fp32" else dict(rtol=8e-3, atol=1e-3)))
     # a timestep outside the table poisons its row instead of reading past the table
     t_bad = t.clone()
     t_bad[2] = 1000
