@@ -6,11 +6,12 @@
 //        sweep 1 (forward): recompute the recurrence, store the state at every chunk boundary (DM_BWD_CH = 4 tokens) in a
 //        workspace -- SKIPPED when the training forward already wrote these checkpoints (dm_mamba1_group.chunk_states,
 //        states_valid = 1: the normal case under autograd_ops.Mamba1ScanFn)
-//        sweep 2 (reverse, chunk by chunk): reload the boundary state, recompute the chunk's states into shared
-//        memory, then run the adjoint recurrence  dh_{j-1} = a_j dh_j,  dh_j += dy_j C_j  backwards, producing
-//        dz, du (scan part), d(delta_raw) per token, dB/dC (reduced over the warp's 32 channels through a shared
-//        transposition, then one atomic per value), and dA / dD / d(dt_bias) accumulated in registers.  Chunk inputs
-//        (x_dbl rows, u, z, dout) are staged by cp.async, double buffered, the scan-order lookup one chunk ahead.
+//        sweep 2 (reverse, chunk by chunk): the chunk's checkpoint, x_dbl rows, u, z and dout are staged by cp.async (double
+//        buffered, the scan-order lookup one chunk ahead); recompute the chunk's states into shared memory (packed pairs of
+//        states), then run the adjoint recurrence  dh_{j-1} = a_j dh_j,  dh_j += dy_j C_j  backwards on packed fp32x2 math,
+//        producing dz, du (scan part), d(delta_raw) per token, dB/dC (bf16 activations: column sums of a [channel][value]
+//        matrix by an all-ones MMA read with ldmatrix.trans; fp32 activations: fp32 transposition; then one atomic per
+//        value), and dA / dD / d(dt_bias) accumulated in registers.  dout may be broadcast over the directions (stride 0).
 //   m1_conv_bwd_kernel   one thread per (sequence, channel): recompute the conv pre-activation, dc = du * silu'(c),
 //        dx by the 4-tap correlation with a sliding window of dc, dw / dbias accumulated and added atomically.
 //
