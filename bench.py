@@ -225,6 +225,7 @@ def kernel_roofline(args, device, peaks, batch=None, input_size=None, mamba2=Non
         # polynomial on the FMA pipe, DM_POLY_PAIRS = 1 in csrc/dm_mamba1.cu) + the gate's tanh; with the delta hand-over
         # the softplus (2 more) runs in m1_delta_kernel
         exps = token_scans * D * (15 if delta is not None else 17)
+        fma_exps = token_scans * D * 2                # the decay pair evaluated by the FMA-pipe polynomial
     else:
         upstream = None
         Cin = 2 * D + 32 + 16
@@ -246,6 +247,7 @@ def kernel_roofline(args, device, peaks, batch=None, input_size=None, mamba2=Non
         bytes_per = (2 * D + 32 + 16) * 2 + D * 2     # read z, x, B, C, dt ; write v
         dom, t = "m2_ssd_kernel", res["m2_ssd_kernel"]
         exps = token_scans * D * 6
+        fma_exps = 0
     achieved = token_scans * bytes_per / t / 1e9
     peak = peaks.get("hbm_gbs", 6650.0)
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)
@@ -267,7 +269,9 @@ def kernel_roofline(args, device, peaks, batch=None, input_size=None, mamba2=Non
             "binding_pipe": "mufu" if not mamba2 else "fp32", "upstream_cuda_scan": upstream,
             "mufu": {"achieved_gexp_s": round(exps / t / 1e9, 1), "peak_gexp_s": round(mufu_peak / 1e9, 1),
                      "frac": round(exps / t / mufu_peak, 4),
-                     "note": "148 SM x 16 MUFU/clk x sm_max_mhz; the scan is instruction-bound on this pipe (DESIGN.md)"}}
+                     "frac_counting_fma_pipe_exponentials": round((exps + fma_exps) / t / mufu_peak, 4),
+                     "note": "148 SM x 16 MUFU/clk x sm_max_mhz; the scan is instruction-bound on this pipe (DESIGN.md); "
+                             "`frac` counts the MUFU ops issued, the second figure also the exponentials moved to the FMA pipe"}}
 
 
 def cpu_model_name():
