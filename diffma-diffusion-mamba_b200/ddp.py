@@ -137,7 +137,9 @@ class FlatTrainState:
     def begin_step(self) -> None:
         """Zero the flat gradient buffer with one kernel, re-arm the buckets and clear every ``.grad``: autograd then hands
         its result tensors over as they are (no accumulate kernel per parameter); ``_flush`` copies them into the flat
-        buffer bucket by bucket and ``finish_backward`` points every ``.grad`` at its (reduced) slot again."""
+        buffer bucket by bucket and ``finish_backward`` points every ``.grad`` at its (reduced) slot again.  One ``backward()`` per
+        ``begin_step()``: gradient accumulation over several backward passes is not supported by this state (the reference's
+        loop, train.py:252-264, does one backward per optimizer step as well)."""
         self.flat_g.zero_()
         self._pending = [b[2] for b in self.buckets]
         self._fired = [False] * len(self.buckets)
