@@ -28,6 +28,11 @@
 // [dt_low hi | dt_low lo | B | C].  W_x lives in shared memory as 16 slices of [64 rows (N) x 64 bf16] (8 KB each, same
 // swizzle), loaded once per CTA and group with 16-byte cp.async, slice s riding along with the x rows of slice s of the
 // first tile (the MMA of slice s needs only WX[s]).
+// Small batches (fewer tiles than half the SMs; config C5's batch 8 has 74 tiles for 148 SMs): the <kSplit = true> variant
+// gives a tile to the two CTAs of a cluster -- each convolves 8 of the 16 channel slices and contracts them against its half
+// of W_x (split K), CTA 1 ships its partial accumulator to CTA 0 through distributed shared memory (mapa + st.shared::cluster,
+// a start-of-kernel cluster arrival + one exchange barrier), CTA 0 adds and writes the rows.  42.0 -> 31.7 us for
+// conv + x_proj + delta at batch 8.
 // Conv inner loop (r02 ncu, first version: 407 instructions per warp and slice, a third of the stall samples on the
 // per-token "does a new sequence start here" branch and the dependent shared-memory load behind it; second version: a
 // separate slow path for the ~4 % of segments that contain a sequence start kept the other 15 warps of the CTA waiting at
